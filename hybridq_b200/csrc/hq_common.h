@@ -1,0 +1,61 @@
+// hq_common.h -- structures shared by the host planner (hq_plan.cpp), the CUDA kernels
+// (hq_kernels.cu) and the CPU emulation of the kernel phases used by the unit tests
+// (hq_emu.cpp).  Plain C++14, no CUDA types.
+//
+// Vocabulary (used everywhere in csrc/):
+//   amplitude      one complex number of the state vector (complex64 = 8 B, complex128 = 16 B)
+//   unit           16 bytes of state: 2 amplitudes (complex64, V = 1) or 1 (complex128, V = 0)
+//   tile           the 2^T amplitudes one CTA holds in shared memory: the low L index bits
+//                  (one contiguous "run" of 2^L amplitudes) plus h = T - L arbitrary "high"
+//                  index bits.  A tile is closed under every gate whose targets are tile bits.
+//   pass           one sweep over the whole state (one kernel launch): every tile is loaded
+//                  once, all gates of the pass are applied in shared memory, and the tile is
+//                  written back once.  Algorithmic HBM bytes per pass = 2 * 2^n * sizeof(amp).
+//   gate-apply     one dense 2^k x 2^k matrix applied to the state (the reference's
+//                  apply_U call, /root/reference/include/python_U.cpp:131-143).
+#pragma once
+#include <cstdint>
+
+#define HQ_DTYPE_C64 0
+#define HQ_DTYPE_C128 1
+
+#define HQ_MAX_UNIT_BITS 12   // 2^12 units * 16 B = 64 KiB of shared memory per tile
+#define HQ_MAX_HIGH 10        // at most 2^10 runs per tile
+#define HQ_MAX_K 10           // largest gate handled by the tile kernels
+#define HQ_SMALL_K 4          // k <= 4: register path; k >= 5: two-phase path
+#define HQ_THREADS_LOG2 8
+#define HQ_THREADS (1 << HQ_THREADS_LOG2)
+#define HQ_BIG_ROWS 8         // output rows per thread in the two-phase (k >= 5) path
+
+#define HQ_GATE_SMALL 0
+#define HQ_GATE_BIG 1
+
+struct HqGateDesc {        // 48 bytes, lives in the device program buffer
+  uint32_t k;              // number of target bits
+  uint32_t kind;           // HQ_GATE_SMALL / HQ_GATE_BIG
+  uint32_t mat_off;        // byte offset of the matrix from the program base
+                           //   small: row-major 2^k x 2^k, interleaved (re, im)
+                           //   big  : column-major (transposed), interleaved
+  uint32_t n_free;         // number of entries in q[]
+  uint8_t tpos[16];        // ascending LOCAL amplitude-bit positions of matrix bits 0..k-1
+  uint8_t q[16];           // small: ordering of the non-target local UNIT bits (work-item bit b
+                           //        -> unit bit q[b]); big: non-target local AMPLITUDE bits
+};
+
+struct HqPassHeader {      // passed to the kernel by value
+  uint32_t n_gates;
+  uint32_t tile_bits;      // T, in amplitudes
+  uint32_t n_high;         // h
+  uint32_t gates_off;      // byte offset of HqGateDesc[0] of this pass from the program base
+  uint8_t high_pos[16];    // ascending GLOBAL amplitude-bit positions of tile bits L..T-1
+  // optional local bit permutation applied when the tile is written back (in-place index-bit
+  // swap kernel, replaces /root/reference/include/swap.h): out_local[j] = tile[sigma(j)],
+  // sigma(j) = XOR_i bit_i(j) << perm[i].  has_perm = 0 -> identity.
+  uint32_t has_perm;
+  uint8_t perm[16];
+  uint32_t max_k;          // largest k among the gates of the pass (selects the kernel variant)
+  uint32_t reserved;
+};
+
+static_assert(sizeof(HqGateDesc) == 48, "HqGateDesc layout");
+static_assert(sizeof(HqPassHeader) == 60, "HqPassHeader layout");

@@ -1,0 +1,164 @@
+// hq_emu.cpp -- TEST INFRASTRUCTURE ONLY (built into libhq_emu.so, never loaded by the
+// product).  A host loop plays the threads of one CTA and runs the very same phase
+// functions (hq_tile.cuh) and the very same planner (hq_plan.cpp) as the CUDA build, so the
+// CPU-only test-suite can check the tile/lane/swizzle index math, the fusion planner and
+// the bit-permutation passes against the oracle without a GPU.  It is NOT a fallback: the
+// Python package never imports it and hybridq_b200 fails loudly without the CUDA library.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "hq_plan.h"
+#include "hq_tile.cuh"
+
+namespace {
+
+template <typename T>
+void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned char* prog, const HqPassHeader& ph) {
+  typedef typename hq::Traits<T>::Unit Unit;
+  typedef typename hq::Traits<T>::Cplx Cplx;
+  const int V = hq::Traits<T>::V;
+  const int Tbits = int(ph.tile_bits), h = int(ph.n_high);
+  const int Tu = Tbits - V, Lu = Tbits - h - V;
+  const uint32_t n_units = 1u << Tu;
+  std::vector<Unit> tile(n_units);
+  std::vector<uint64_t> run_off(size_t(1) << h);
+  for (uint32_t r = 0; r < (1u << h); ++r) run_off[r] = hq::deposit(r, ph.high_pos, h) >> V;
+  std::vector<HqGateDesc> gd(ph.n_gates);
+  if (ph.n_gates) memcpy(gd.data(), prog + ph.gates_off, ph.n_gates * sizeof(HqGateDesc));
+  const uint64_t n_tiles = uint64_t(1) << (n - ph.tile_bits);
+  for (uint64_t t = 0; t < n_tiles; ++t) {
+    const uint64_t base_unit = hq::tile_base(t, Tbits, h, ph.high_pos) >> V;
+    for (int tid = 0; tid < HQ_THREADS; ++tid)
+      for (uint32_t c = uint32_t(tid); c < n_units; c += HQ_THREADS)
+        tile[hq::swz(c)] = state[hq::unit_global(c, base_unit, run_off.data(), Lu)];
+    for (uint32_t gi = 0; gi < ph.n_gates; ++gi) {
+      const HqGateDesc& g = gd[gi];
+      if (g.kind == HQ_GATE_SMALL) {
+        for (int tid = 0; tid < HQ_THREADS; ++tid) hq::gate_small_dispatch<4>(tile.data(), g, prog, Tu, tid);
+      } else {
+        const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + g.mat_off);
+        const int rounds = hq::big_rounds(Tbits, int(g.k));
+        std::vector<hq::BigAcc<T>> acc(HQ_THREADS);
+        for (int r = 0; r < rounds; ++r) {
+          for (int tid = 0; tid < HQ_THREADS; ++tid)
+            hq::gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile.data()), g, Ut, Tbits, tid, r, acc[size_t(tid)]);
+          for (int tid = 0; tid < HQ_THREADS; ++tid)
+            hq::gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile.data()), g, acc[size_t(tid)]);
+        }
+      }
+    }
+    if (!ph.has_perm) {
+      for (uint32_t c = 0; c < n_units; ++c)
+        state[hq::unit_global(c, base_unit, run_off.data(), Lu)] = tile[hq::swz(c)];
+    } else {
+      const Cplx* amps = reinterpret_cast<const Cplx*>(tile.data());
+      for (uint32_t c = 0; c < n_units; ++c) {
+        Cplx o[1 << V];
+        for (uint32_t e = 0; e < (1u << V); ++e)
+          o[e] = amps[hq::amp_slot<T>(hq::perm_src((c << V) | e, ph.perm, Tbits))];
+        state[hq::unit_global(c, base_unit, run_off.data(), Lu)] = hq::make_unit(o);
+      }
+    }
+  }
+}
+
+void emu_plan(hq::Plan& plan, void* state) {
+  for (const hq::PassInfo& pi : plan.passes) {
+    if (pi.header.n_gates == 0 && !pi.header.has_perm) continue;
+    if (plan.dtype == HQ_DTYPE_C64)
+      emu_pass<float>(static_cast<float4*>(state), plan.n_qubits, plan.program.data(), pi.header);
+    else
+      emu_pass<double>(static_cast<double2*>(state), plan.n_qubits, plan.program.data(), pi.header);
+  }
+}
+
+hq::PlanOptions make_opts(const int* o) {
+  hq::PlanOptions p;
+  if (o) {
+    p.tile_bits = o[0];
+    p.min_run_bits = o[1];
+    p.fuse = o[2];
+    p.max_gates_per_pass = o[3];
+    p.lookahead = o[4];
+  }
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// opts = {tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead} or NULL.
+// info_out (optional, >= 2 ints) receives {n_passes, n_gates}.
+int hq_emu_run_circuit(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
+                       const double* U_flat, const int* opts, void* state_interleaved, int* info_out,
+                       char* err, int err_len) {
+  std::vector<hq::GateIn> gates(n_gates);
+  size_t po = 0, uo = 0;
+  for (unsigned g = 0; g < n_gates; ++g) {
+    const unsigned k = ks[g];
+    gates[g].k = k;
+    gates[g].pos.assign(pos_flat + po, pos_flat + po + k);
+    const size_t e = size_t(1) << (2 * k);
+    gates[g].U.resize(e);
+    for (size_t i = 0; i < e; ++i) gates[g].U[i] = std::complex<double>(U_flat[uo + 2 * i], U_flat[uo + 2 * i + 1]);
+    po += k;
+    uo += 2 * e;
+  }
+  hq::Plan plan;
+  if (hq::plan_build(plan, dtype, n, gates, make_opts(opts))) {
+    if (err) snprintf(err, size_t(err_len), "%s", plan.error.c_str());
+    return 1;
+  }
+  emu_plan(plan, state_interleaved);
+  if (info_out) {
+    info_out[0] = int(plan.passes.size());
+    info_out[1] = int(plan.n_gates);
+  }
+  return 0;
+}
+
+int hq_emu_bitperm(int dtype, unsigned n, const unsigned* perm, const int* opts, void* state_interleaved,
+                   int* info_out, char* err, int err_len) {
+  hq::Plan plan;
+  std::vector<unsigned> pf(perm, perm + n);
+  if (hq::plan_build_bitperm(plan, dtype, n, pf, make_opts(opts))) {
+    if (err) snprintf(err, size_t(err_len), "%s", plan.error.c_str());
+    return 1;
+  }
+  emu_plan(plan, state_interleaved);
+  if (info_out) info_out[0] = int(plan.passes.size());
+  return 0;
+}
+
+// planner introspection for host-logic tests: passes as flat records
+// {tile_bits, n_high, n_gates, has_perm, high_pos..., gate ids...}; returns words written or -1.
+int hq_emu_plan_dump(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
+                     const int* opts, unsigned* out, int out_len) {
+  std::vector<hq::GateIn> gates(n_gates);
+  size_t po = 0;
+  for (unsigned g = 0; g < n_gates; ++g) {
+    const unsigned k = ks[g];
+    gates[g].k = k;
+    gates[g].pos.assign(pos_flat + po, pos_flat + po + k);
+    gates[g].U.assign(size_t(1) << (2 * k), std::complex<double>(0, 0));
+    po += k;
+  }
+  hq::Plan plan;
+  if (hq::plan_build(plan, dtype, n, gates, make_opts(opts))) return -1;
+  int w = 0;
+  for (const hq::PassInfo& pi : plan.passes) {
+    const int need = 4 + int(pi.header.n_high) + int(pi.gate_ids.size());
+    if (w + need > out_len) return -1;
+    out[w++] = pi.header.tile_bits;
+    out[w++] = pi.header.n_high;
+    out[w++] = pi.header.n_gates;
+    out[w++] = pi.header.has_perm;
+    for (unsigned i = 0; i < pi.header.n_high; ++i) out[w++] = pi.header.high_pos[i];
+    for (unsigned id : pi.gate_ids) out[w++] = id;
+  }
+  return w;
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+// hq_plan.cpp -- see hq_plan.h.
+#include "hq_plan.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace hq {
+
+int default_tile_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 12 : 11; }   // 32 KiB tiles
+int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 4; }  // 256-byte runs
+
+namespace {
+
+const int kMaxGatesPerPass = 48;
+
+int vbits(int dtype) { return dtype == HQ_DTYPE_C64 ? 1 : 0; }
+int max_tile_bits(int dtype) { return HQ_MAX_UNIT_BITS + vbits(dtype); }
+
+// Largest run length L in [Lmin, T] such that the members of `bits` at or above L fit in the
+// T - L high slots.  Returns -1 if there is none.
+int choose_run_bits(const std::vector<unsigned>& bits_sorted, int T, int Lmin) {
+  for (int L = T; L >= Lmin; --L) {
+    int high = 0;
+    for (unsigned b : bits_sorted) high += (int(b) >= L);
+    if (high <= T - L && high <= HQ_MAX_HIGH) return L;
+  }
+  return -1;
+}
+
+struct Canon {               // gate with ascending positions and accordingly permuted matrix
+  unsigned k;
+  std::vector<unsigned> pos;
+  std::vector<std::complex<double>> U;
+};
+
+bool canonicalise(const GateIn& g, unsigned n, Canon& out, std::string& err) {
+  const unsigned k = g.k;
+  if (g.pos.size() != k || g.U.size() != (size_t(1) << (2 * k))) {
+    err = "gate has inconsistent k / pos / U sizes";
+    return false;
+  }
+  std::vector<unsigned> order(k);
+  for (unsigned i = 0; i < k; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return g.pos[a] < g.pos[b]; });
+  out.k = k;
+  out.pos.resize(k);
+  for (unsigned i = 0; i < k; ++i) {
+    out.pos[i] = g.pos[order[i]];
+    if (out.pos[i] >= n) { err = "gate position out of range"; return false; }
+    if (i && out.pos[i] == out.pos[i - 1]) { err = "gate has duplicate positions"; return false; }
+  }
+  const size_t dim = size_t(1) << k;
+  // new matrix bit i is old matrix bit order[i]
+  std::vector<size_t> map(dim);
+  for (size_t a = 0; a < dim; ++a) {
+    size_t o = 0;
+    for (unsigned i = 0; i < k; ++i) o |= ((a >> i) & 1u) << order[i];
+    map[a] = o;
+  }
+  out.U.resize(dim * dim);
+  for (size_t a = 0; a < dim; ++a)
+    for (size_t b = 0; b < dim; ++b) out.U[a * dim + b] = g.U[map[a] * dim + map[b]];
+  return true;
+}
+
+// Choose the tile of a pass: pad the mandatory high bits up to exactly T - L entries.
+void make_tile(const std::vector<unsigned>& bits_sorted, int T, int L, unsigned n, HqPassHeader& ph) {
+  std::vector<unsigned> high;
+  for (unsigned b : bits_sorted)
+    if (int(b) >= L) high.push_back(b);
+  const int want = T - L;
+  for (unsigned b = unsigned(L); int(high.size()) < want && b < n; ++b)
+    if (std::find(high.begin(), high.end(), b) == high.end()) high.push_back(b);
+  std::sort(high.begin(), high.end());
+  memset(&ph, 0, sizeof(ph));
+  ph.tile_bits = uint32_t(L + int(high.size()));
+  ph.n_high = uint32_t(high.size());
+  for (size_t i = 0; i < high.size(); ++i) ph.high_pos[i] = uint8_t(high[i]);
+}
+
+int local_bit(const HqPassHeader& ph, unsigned global_bit) {
+  const int L = int(ph.tile_bits) - int(ph.n_high);
+  if (int(global_bit) < L) return int(global_bit);
+  for (unsigned i = 0; i < ph.n_high; ++i)
+    if (ph.high_pos[i] == global_bit) return L + int(i);
+  return -1;
+}
+
+// Order the free bits so that the three lowest work-item bits land on bits with distinct
+// residues mod 3 (conflict-free quarter-warps under swz), lowest bits first otherwise.
+std::vector<unsigned> lane_order(const std::vector<unsigned>& free_sorted) {
+  std::vector<unsigned> first;
+  bool used_res[3] = {false, false, false};
+  std::vector<bool> taken(free_sorted.size(), false);
+  for (size_t i = 0; i < free_sorted.size() && first.size() < 3; ++i) {
+    const unsigned r = free_sorted[i] % 3;
+    if (!used_res[r]) {
+      used_res[r] = true;
+      taken[i] = true;
+      first.push_back(free_sorted[i]);
+    }
+  }
+  std::vector<unsigned> out = first;
+  for (size_t i = 0; i < free_sorted.size(); ++i)
+    if (!taken[i]) out.push_back(free_sorted[i]);
+  return out;
+}
+
+template <typename R>
+void write_matrix(std::vector<unsigned char>& prog, size_t off, const Canon& c, bool transposed) {
+  const size_t dim = size_t(1) << c.k;
+  R* dst = reinterpret_cast<R*>(prog.data() + off);
+  for (size_t i = 0; i < dim; ++i)
+    for (size_t j = 0; j < dim; ++j) {
+      const std::complex<double> v = c.U[i * dim + j];
+      const size_t e = transposed ? (j * dim + i) : (i * dim + j);
+      dst[2 * e] = R(v.real());
+      dst[2 * e + 1] = R(v.imag());
+    }
+}
+
+}  // namespace
+
+int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gates_in,
+               const PlanOptions& opts) {
+  plan.dtype = dtype;
+  plan.n_qubits = n;
+  plan.passes.clear();
+  plan.program.clear();
+  plan.error.clear();
+  plan.n_gates = 0;
+  const int V = vbits(dtype);
+  if (dtype != HQ_DTYPE_C64 && dtype != HQ_DTYPE_C128) { plan.error = "bad dtype"; return 1; }
+  if (n < unsigned(V) + 0u || n == 0 || n > 48) { plan.error = "unsupported number of qubits"; return 1; }
+
+  int T = opts.tile_bits > 0 ? opts.tile_bits : default_tile_bits(dtype);
+  T = std::min(T, max_tile_bits(dtype));
+  T = std::min<int>(T, int(n));
+  if (T < V) { plan.error = "tile too small"; return 1; }
+  const int hard_min_run = V;                       // a unit must not straddle two runs
+  int fuse_min_run = opts.min_run_bits >= 0 ? opts.min_run_bits : default_min_run_bits(dtype);
+  fuse_min_run = std::max(hard_min_run, std::min(fuse_min_run, T));
+  const int max_per_pass = std::min(kMaxGatesPerPass, opts.max_gates_per_pass > 0 ? opts.max_gates_per_pass : kMaxGatesPerPass);
+  const size_t lookahead = opts.lookahead > 0 ? size_t(opts.lookahead) : size_t(4096);
+
+  // canonical gates (k = 0 gates are no-ops exactly as in the reference, python_U.cpp:38-39)
+  std::vector<Canon> canon;
+  std::vector<unsigned> canon_id;
+  for (size_t i = 0; i < gates_in.size(); ++i) {
+    if (gates_in[i].k == 0) continue;
+    if (gates_in[i].k > HQ_MAX_K) { plan.error = "gate with k > HQ_MAX_K"; return 1; }
+    Canon c;
+    if (!canonicalise(gates_in[i], n, c, plan.error)) return 1;
+    std::vector<unsigned> b = c.pos;
+    if (choose_run_bits(b, T, hard_min_run) < 0) { plan.error = "gate does not fit in a tile"; return 1; }
+    canon.push_back(std::move(c));
+    canon_id.push_back(unsigned(i));
+  }
+  plan.n_gates = unsigned(canon.size());
+
+  // ---- greedy fusion: a gate joins the open pass if it touches no bit a deferred gate
+  // touches and the union of target bits still fits in a tile with runs >= fuse_min_run.
+  std::vector<bool> done(canon.size(), false);
+  size_t first = 0;
+  struct Draft { std::vector<unsigned> ids; std::vector<unsigned> bits; };
+  std::vector<Draft> drafts;
+  while (first < canon.size()) {
+    if (done[first]) { ++first; continue; }
+    Draft d;
+    uint64_t blocked = 0;
+    std::vector<unsigned> bits;
+    size_t scanned_blocked = 0;
+    for (size_t i = first; i < canon.size(); ++i) {
+      if (done[i]) continue;
+      uint64_t mask = 0;
+      for (unsigned p : canon[i].pos) mask |= uint64_t(1) << p;
+      bool take = !(mask & blocked) && int(d.ids.size()) < max_per_pass;
+      if (take) {
+        std::vector<unsigned> u = bits;
+        for (unsigned p : canon[i].pos)
+          if (std::find(u.begin(), u.end(), p) == u.end()) u.push_back(p);
+        std::sort(u.begin(), u.end());
+        const int minrun = d.ids.empty() ? hard_min_run : fuse_min_run;
+        if (choose_run_bits(u, T, minrun) >= 0) {
+          bits.swap(u);
+          d.ids.push_back(unsigned(i));
+          done[i] = true;
+        } else {
+          take = false;
+        }
+      }
+      if (!take) {
+        blocked |= mask;
+        if (++scanned_blocked >= lookahead) break;
+      }
+      if (!opts.fuse && !d.ids.empty()) break;
+      if (blocked == ((n >= 64) ? ~uint64_t(0) : ((uint64_t(1) << n) - 1))) break;
+    }
+    d.bits = bits;
+    drafts.push_back(std::move(d));
+  }
+
+  // ---- serialise
+  size_t total_gates = 0;
+  for (const Draft& d : drafts) total_gates += d.ids.size();
+  size_t off = total_gates * sizeof(HqGateDesc);
+  off = (off + 15) & ~size_t(15);
+  const size_t mat_base = off;
+  size_t mat_bytes = 0;
+  const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
+  for (const Canon& c : canon) mat_bytes += ((esz << (2 * c.k)) + 15) & ~size_t(15);
+  plan.program.assign(mat_base + mat_bytes + 16, 0);
+
+  size_t gate_cursor = 0;
+  size_t mat_cursor = mat_base;
+  for (const Draft& d : drafts) {
+    PassInfo pi;
+    // single gates may use shorter runs than the fuser is allowed to create
+    int L = choose_run_bits(d.bits, T, d.ids.size() > 1 ? fuse_min_run : hard_min_run);
+    if (L < 0) { plan.error = "internal: pass does not fit"; return 1; }
+    make_tile(d.bits, T, L, n, pi.header);
+    pi.header.n_gates = uint32_t(d.ids.size());
+    pi.header.gates_off = uint32_t(gate_cursor * sizeof(HqGateDesc));
+    const int Tbits = int(pi.header.tile_bits);
+    const int Tu = Tbits - V;
+    for (unsigned id : d.ids) {
+      const Canon& c = canon[id];
+      HqGateDesc gd;
+      memset(&gd, 0, sizeof(gd));
+      gd.k = c.k;
+      gd.kind = c.k <= HQ_SMALL_K ? HQ_GATE_SMALL : HQ_GATE_BIG;
+      gd.mat_off = uint32_t(mat_cursor);
+      std::vector<bool> is_t;
+      is_t.assign(size_t(Tbits), false);
+      for (unsigned i = 0; i < c.k; ++i) {
+        const int lb = local_bit(pi.header, c.pos[i]);
+        if (lb < 0) { plan.error = "internal: target bit outside tile"; return 1; }
+        gd.tpos[i] = uint8_t(lb);
+        is_t[size_t(lb)] = true;
+      }
+      // canonical positions are ascending globally, hence ascending locally too
+      std::vector<unsigned> free_bits;
+      if (gd.kind == HQ_GATE_SMALL) {
+        for (int u = 0; u < Tu; ++u)
+          if (!is_t[size_t(u + V)]) free_bits.push_back(unsigned(u));
+        free_bits = lane_order(free_bits);
+      } else {
+        for (int a = 0; a < Tbits; ++a)
+          if (!is_t[size_t(a)]) free_bits.push_back(unsigned(a));
+      }
+      gd.n_free = uint32_t(free_bits.size());
+      for (size_t i = 0; i < free_bits.size() && i < 16; ++i) gd.q[i] = uint8_t(free_bits[i]);
+      memcpy(plan.program.data() + gate_cursor * sizeof(HqGateDesc), &gd, sizeof(gd));
+      if (dtype == HQ_DTYPE_C64)
+        write_matrix<float>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
+      else
+        write_matrix<double>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
+      mat_cursor += ((esz << (2 * c.k)) + 15) & ~size_t(15);
+      ++gate_cursor;
+      pi.gate_ids.push_back(canon_id[id]);
+      pi.header.max_k = std::max<uint32_t>(pi.header.max_k, c.k);
+    }
+    plan.passes.push_back(std::move(pi));
+  }
+  return 0;
+}
+
+int plan_build_bitperm(Plan& plan, int dtype, unsigned n, const std::vector<unsigned>& perm_full,
+                       const PlanOptions& opts) {
+  plan.dtype = dtype;
+  plan.n_qubits = n;
+  plan.passes.clear();
+  plan.program.assign(16, 0);
+  plan.error.clear();
+  plan.n_gates = 0;
+  const int V = vbits(dtype);
+  if (perm_full.size() != n) { plan.error = "permutation must list every bit"; return 1; }
+  {
+    std::vector<bool> seen(n, false);
+    for (unsigned p : perm_full) {
+      if (p >= n || seen[p]) { plan.error = "not a permutation"; return 1; }
+      seen[p] = true;
+    }
+  }
+  int T = opts.tile_bits > 0 ? opts.tile_bits : default_tile_bits(dtype);
+  T = std::min(T, max_tile_bits(dtype));
+  T = std::min<int>(T, int(n));
+  const int hard_min_run = V;
+  int min_run = opts.min_run_bits >= 0 ? opts.min_run_bits : default_min_run_bits(dtype);
+  min_run = std::max(hard_min_run, std::min(min_run, T));
+
+  // decompose into transpositions of positions: cur[b] = old bit currently at position b
+  std::vector<unsigned> cur(n);
+  for (unsigned b = 0; b < n; ++b) cur[b] = b;
+  std::vector<std::pair<unsigned, unsigned>> swaps;
+  for (unsigned i = 0; i < n; ++i) {
+    if (cur[i] == perm_full[i]) continue;
+    unsigned j = i;
+    while (cur[j] != perm_full[i]) ++j;
+    std::swap(cur[i], cur[j]);
+    swaps.push_back({i, j});
+  }
+  // group consecutive transpositions whose bits fit one tile
+  size_t s = 0;
+  while (s < swaps.size()) {
+    std::vector<unsigned> bits;
+    size_t e = s;
+    while (e < swaps.size()) {
+      std::vector<unsigned> u = bits;
+      for (unsigned b : {swaps[e].first, swaps[e].second})
+        if (std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
+      std::sort(u.begin(), u.end());
+      const int mr = (e == s) ? hard_min_run : min_run;
+      if (choose_run_bits(u, T, mr) < 0) break;
+      bits.swap(u);
+      ++e;
+    }
+    if (e == s) { plan.error = "transposition does not fit in a tile"; return 1; }
+    PassInfo pi;
+    const int L = choose_run_bits(bits, T, (e - s) > 1 ? min_run : hard_min_run);
+    make_tile(bits, T, L, n, pi.header);
+    const int Tbits = int(pi.header.tile_bits);
+    // compose: total[i] = p1[p2[...pk[i]]] where stage r has new bit a <- old bit b and vice versa
+    std::vector<unsigned> total;
+    total.resize(size_t(Tbits));
+    for (int i = 0; i < Tbits; ++i) total[size_t(i)] = unsigned(i);
+    for (size_t r = e; r-- > s;) {
+      const int a = local_bit(pi.header, swaps[r].first);
+      const int b = local_bit(pi.header, swaps[r].second);
+      for (int i = 0; i < Tbits; ++i) {
+        if (total[size_t(i)] == unsigned(a)) total[size_t(i)] = unsigned(b);
+        else if (total[size_t(i)] == unsigned(b)) total[size_t(i)] = unsigned(a);
+      }
+    }
+    pi.header.has_perm = 1;
+    for (int i = 0; i < Tbits; ++i) pi.header.perm[i] = uint8_t(total[size_t(i)]);
+    pi.header.n_gates = 0;
+    pi.header.gates_off = 0;
+    plan.passes.push_back(std::move(pi));
+    s = e;
+  }
+  return 0;
+}
+
+}  // namespace hq

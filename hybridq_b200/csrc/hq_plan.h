@@ -1,0 +1,63 @@
+// hq_plan.h -- host-side planner: turns a stream of gate-applies into passes of the tile
+// kernel (which gates share a pass, which index bits form the tile, how work items map to
+// lanes) and serialises them into the program buffer the kernel reads.  Pure C++ (no CUDA),
+// so the CPU-only test-suite exercises it directly.
+//
+// This is the B200-native counterpart of the bookkeeping the reference does per gate in
+// Python (/root/reference/hybridq/circuit/simulation/simulation.py:556-646: low-bit swap
+// windows, _map/_inv_map, one ctypes call per gate): here nothing is ever permuted in
+// memory for a gate, high target bits become tile bits instead.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "hq_common.h"
+
+namespace hq {
+
+struct GateIn {
+  unsigned k = 0;
+  std::vector<unsigned> pos;                 // pos[i] = amplitude-index bit of matrix bit i
+  std::vector<std::complex<double>> U;       // row-major 2^k x 2^k
+};
+
+struct PlanOptions {
+  int tile_bits = 0;        // T in amplitudes; 0 = default for the dtype
+  int min_run_bits = -1;    // smallest run (log2 amplitudes) the fuser may create; -1 = default
+  int fuse = 1;             // 0: one gate per pass
+  int max_gates_per_pass = 0;   // 0 = default (48)
+  int lookahead = 0;        // how many gates past the first blocked one the fuser scans; 0 = default
+};
+
+struct PassInfo {
+  HqPassHeader header;
+  std::vector<unsigned> gate_ids;            // indices into the input gate list
+};
+
+struct Plan {
+  int dtype = HQ_DTYPE_C64;
+  unsigned n_qubits = 0;
+  unsigned n_gates = 0;                      // gate-applies covered (k = 0 gates are dropped)
+  std::vector<PassInfo> passes;
+  std::vector<unsigned char> program;        // host copy of the device program buffer
+  std::string error;
+  // device side (filled by hq_abi.cu)
+  void* d_program = nullptr;
+  int device = -1;
+};
+
+int default_tile_bits(int dtype);
+int default_min_run_bits(int dtype);
+
+// Build a plan.  Returns 0 on success; on failure returns non-zero and sets plan.error.
+int plan_build(Plan& plan, int dtype, unsigned n_qubits, const std::vector<GateIn>& gates,
+               const PlanOptions& opts);
+
+// A single pass whose only job is an in-place permutation of index bits:
+// new bit i <- old bit perm[i] for the bits listed (a closed set of at most T bits).
+int plan_build_bitperm(Plan& plan, int dtype, unsigned n_qubits, const std::vector<unsigned>& perm_full,
+                       const PlanOptions& opts);
+
+}  // namespace hq

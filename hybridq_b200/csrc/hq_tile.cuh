@@ -1,0 +1,426 @@
+// hq_tile.cuh -- the phases of the tile kernel, written once and compiled twice:
+//   * by nvcc for sm_100a inside hq_kernels.cu (the product), and
+//   * by g++ inside hq_emu.cpp, where a host loop plays the role of the threads of one CTA
+//     (test infrastructure only; lets the CPU-only test-suite check the index math).
+//
+// What the kernel computes is the reference's U::apply (/root/reference/include/U.h:28-102,
+// :123-202): for every group of 2^k amplitudes that differ only in the k target bits,
+// psi' = U psi, in place.  HOW it is computed is B200-first and shares nothing with the
+// reference: the state is interleaved complex in HBM, a CTA stages a tile of 2^T amplitudes
+// in shared memory with 16-byte cp.async copies of whole contiguous runs (so global traffic
+// is fully coalesced whatever the target bits are), applies every gate of the pass to the
+// tile from registers, and writes the tile back once.
+//
+// Shared-memory layout: the tile is an array of 16-byte units indexed by the local unit
+// index u; unit u lives at physical slot swz(u).  swz XOR-folds unit bits 3-5, 6-8 and 9-11
+// onto bits 0-2, which is GF(2)-linear (swz(a ^ b) = swz(a) ^ swz(b)), keeps 8 consecutive
+// units in 8 distinct 16-byte bank groups (conflict-free fills and drains), and makes a
+// quarter-warp of LDS.128 conflict-free whenever the three lowest work-item bits are mapped
+// (by HqGateDesc::q, chosen on the host) to unit bits with distinct residues mod 3.
+#pragma once
+#include "hq_common.h"
+
+#ifdef __CUDACC__
+#define HQ_DEV __device__ __forceinline__
+#define HQ_HD __host__ __device__ __forceinline__
+#define HQ_LDG(p) __ldg(p)
+#define HQ_UNROLL _Pragma("unroll")
+#define HQ_NOUNROLL _Pragma("unroll 1")
+#else
+#define HQ_DEV inline
+#define HQ_HD inline
+#define HQ_LDG(p) (*(p))
+#define HQ_UNROLL
+#define HQ_NOUNROLL
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline double2 make_double2(double a, double b) { return double2{a, b}; }
+#endif
+
+namespace hq {
+
+template <typename T> struct Traits;
+template <> struct Traits<float> {
+  typedef float4 Unit;      // 2 amplitudes: (x, y) = even amplitude re/im, (z, w) = odd
+  typedef float2 Cplx;
+  static const int V = 1;   // log2(amplitudes per unit)
+};
+template <> struct Traits<double> {
+  typedef double2 Unit;     // 1 amplitude
+  typedef double2 Cplx;
+  static const int V = 0;
+};
+
+HQ_HD uint32_t swz(uint32_t u) {
+  return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u) ^ ((u >> 9) & 7u);
+}
+
+// Open a zero gap at every position of `pos` (ascending, final coordinates).
+HQ_HD uint64_t open_gaps(uint64_t x, const uint8_t* pos, int n) {
+  for (int i = 0; i < n; ++i) {
+    const uint64_t low = (uint64_t(1) << pos[i]) - 1;
+    x = ((x & ~low) << 1) | (x & low);
+  }
+  return x;
+}
+
+HQ_HD uint64_t deposit(uint32_t m, const uint8_t* pos, int n) {
+  uint64_t y = 0;
+  for (int i = 0; i < n; ++i) y |= uint64_t((m >> i) & 1u) << pos[i];
+  return y;
+}
+
+// First amplitude index of tile `t`.
+HQ_HD uint64_t tile_base(uint64_t t, int tile_bits, int n_high, const uint8_t* high_pos) {
+  return open_gaps(t << (tile_bits - n_high), high_pos, n_high);
+}
+
+// ---------------------------------------------------------------------------------------
+// complex helpers
+// ---------------------------------------------------------------------------------------
+template <typename R>
+HQ_DEV void cmac(R& ar, R& ai, R ur, R ui, R xr, R xi) {
+  // same operation order as the reference inner loop (U.h:93-94)
+  ar += ur * xr - ui * xi;
+  ai += ur * xi + ui * xr;
+}
+
+// XOR of s[i] over the set bits of m.
+template <int KK>
+HQ_DEV uint32_t xoff(uint32_t m, const uint32_t* s) {
+  uint32_t o = 0;
+  HQ_UNROLL
+  for (int i = 0; i < KK; ++i) o ^= ((m >> i) & 1u) ? s[i] : 0u;
+  return o;
+}
+
+// Work item w (bits [0, n_free)) -> local unit/amp index with zeros at the target bits.
+// The low `tb` bits come from `lo` (the thread id), the rest from `hi` (the iteration).
+HQ_DEV uint32_t scatter_bits(uint32_t w, const uint8_t* q, int from, int to) {
+  uint32_t u = 0;
+  for (int b = from; b < to; ++b) u |= ((w >> (b - from)) & 1u) << q[b];
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------
+// register path, complex64, no target on amplitude bit 0: KK unit-level target bits,
+// every thread handles two groups at once (the even and the odd amplitude of its units).
+// ---------------------------------------------------------------------------------------
+template <int KK>
+HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc& g, const float2* __restrict__ U,
+                           int Tu, int tid) {
+  const int DIM = 1 << KK;
+  const int nq = Tu - KK;
+  const uint32_t nwork = 1u << nq;
+  if (uint32_t(tid) >= nwork) return;
+  uint32_t s[KK > 0 ? KK : 1];
+  HQ_UNROLL
+  for (int i = 0; i < KK; ++i) s[i] = swz(1u << (g.tpos[i] - 1));
+  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
+  const uint32_t ut = scatter_bits(uint32_t(tid), g.q, 0, tb);
+  const uint32_t niter = nwork >> tb;
+
+  float2 Ur[KK <= 2 ? DIM * DIM : 1];
+  if (KK <= 2) {
+    HQ_UNROLL
+    for (int e = 0; e < DIM * DIM; ++e) Ur[e] = HQ_LDG(&U[e]);
+  }
+
+  HQ_NOUNROLL
+  for (uint32_t it = 0; it < niter; ++it) {
+    const uint32_t sb = swz(ut | scatter_bits(it, g.q, tb, nq));
+    float4 in[DIM];
+    HQ_UNROLL
+    for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xoff<KK>(m, s)];
+    if (KK <= 2) {
+      HQ_UNROLL
+      for (int i = 0; i < DIM; ++i) {
+        float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+        HQ_UNROLL
+        for (int j = 0; j < DIM; ++j) {
+          const float2 u = Ur[i * DIM + j];
+          cmac(a0r, a0i, u.x, u.y, in[j].x, in[j].y);
+          cmac(a1r, a1i, u.x, u.y, in[j].z, in[j].w);
+        }
+        tile[sb ^ xoff<KK>(i, s)] = make_float4(a0r, a0i, a1r, a1i);
+      }
+    } else {
+      HQ_NOUNROLL
+      for (int i = 0; i < DIM; ++i) {
+        float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+        const float4* row = reinterpret_cast<const float4*>(U + i * DIM);
+        HQ_UNROLL
+        for (int j = 0; j < DIM; j += 2) {
+          const float4 u = HQ_LDG(&row[j >> 1]);
+          cmac(a0r, a0i, u.x, u.y, in[j].x, in[j].y);
+          cmac(a1r, a1i, u.x, u.y, in[j].z, in[j].w);
+          cmac(a0r, a0i, u.z, u.w, in[j + 1].x, in[j + 1].y);
+          cmac(a1r, a1i, u.z, u.w, in[j + 1].z, in[j + 1].w);
+        }
+        tile[sb ^ xoff<KK>(uint32_t(i), s)] = make_float4(a0r, a0i, a1r, a1i);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// register path, complex64, matrix bit 0 sits on amplitude bit 0 (inside the unit):
+// K = KK + 1 matrix bits, one group per thread, amplitude m = unit (m >> 1) half (m & 1).
+// ---------------------------------------------------------------------------------------
+template <int KK>
+HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc& g, const float2* __restrict__ U,
+                               int Tu, int tid) {
+  const int UD = 1 << KK;        // units per group
+  const int DIM = 2 << KK;       // amplitudes per group
+  const int nq = Tu - KK;
+  const uint32_t nwork = 1u << nq;
+  if (uint32_t(tid) >= nwork) return;
+  uint32_t s[KK > 0 ? KK : 1];
+  HQ_UNROLL
+  for (int i = 0; i < KK; ++i) s[i] = swz(1u << (g.tpos[i + 1] - 1));
+  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
+  const uint32_t ut = scatter_bits(uint32_t(tid), g.q, 0, tb);
+  const uint32_t niter = nwork >> tb;
+
+  float2 Ur[KK <= 1 ? DIM * DIM : 1];
+  if (KK <= 1) {
+    HQ_UNROLL
+    for (int e = 0; e < DIM * DIM; ++e) Ur[e] = HQ_LDG(&U[e]);
+  }
+
+  HQ_NOUNROLL
+  for (uint32_t it = 0; it < niter; ++it) {
+    const uint32_t sb = swz(ut | scatter_bits(it, g.q, tb, nq));
+    float4 in[UD];
+    HQ_UNROLL
+    for (int m = 0; m < UD; ++m) in[m] = tile[sb ^ xoff<KK>(m, s)];
+    if (KK <= 1) {
+      HQ_UNROLL
+      for (int iu = 0; iu < UD; ++iu) {
+        float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+        HQ_UNROLL
+        for (int ju = 0; ju < UD; ++ju) {
+          const float2 u00 = Ur[(2 * iu) * DIM + 2 * ju], u01 = Ur[(2 * iu) * DIM + 2 * ju + 1];
+          const float2 u10 = Ur[(2 * iu + 1) * DIM + 2 * ju], u11 = Ur[(2 * iu + 1) * DIM + 2 * ju + 1];
+          cmac(a0r, a0i, u00.x, u00.y, in[ju].x, in[ju].y);
+          cmac(a0r, a0i, u01.x, u01.y, in[ju].z, in[ju].w);
+          cmac(a1r, a1i, u10.x, u10.y, in[ju].x, in[ju].y);
+          cmac(a1r, a1i, u11.x, u11.y, in[ju].z, in[ju].w);
+        }
+        tile[sb ^ xoff<KK>(iu, s)] = make_float4(a0r, a0i, a1r, a1i);
+      }
+    } else {
+      HQ_NOUNROLL
+      for (int iu = 0; iu < UD; ++iu) {
+        float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+        const float4* r0 = reinterpret_cast<const float4*>(U + (2 * iu) * DIM);
+        const float4* r1 = reinterpret_cast<const float4*>(U + (2 * iu + 1) * DIM);
+        HQ_UNROLL
+        for (int ju = 0; ju < UD; ++ju) {
+          const float4 ua = HQ_LDG(&r0[ju]);
+          const float4 ub = HQ_LDG(&r1[ju]);
+          cmac(a0r, a0i, ua.x, ua.y, in[ju].x, in[ju].y);
+          cmac(a0r, a0i, ua.z, ua.w, in[ju].z, in[ju].w);
+          cmac(a1r, a1i, ub.x, ub.y, in[ju].x, in[ju].y);
+          cmac(a1r, a1i, ub.z, ub.w, in[ju].z, in[ju].w);
+        }
+        tile[sb ^ xoff<KK>(uint32_t(iu), s)] = make_float4(a0r, a0i, a1r, a1i);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// register path, complex128: unit = amplitude, one group per thread.
+// ---------------------------------------------------------------------------------------
+template <int KK>
+HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc& g, const double2* __restrict__ U,
+                           int Tu, int tid) {
+  const int DIM = 1 << KK;
+  const int nq = Tu - KK;
+  const uint32_t nwork = 1u << nq;
+  if (uint32_t(tid) >= nwork) return;
+  uint32_t s[KK > 0 ? KK : 1];
+  HQ_UNROLL
+  for (int i = 0; i < KK; ++i) s[i] = swz(1u << g.tpos[i]);
+  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
+  const uint32_t ut = scatter_bits(uint32_t(tid), g.q, 0, tb);
+  const uint32_t niter = nwork >> tb;
+
+  double2 Ur[KK <= 1 ? DIM * DIM : 1];
+  if (KK <= 1) {
+    HQ_UNROLL
+    for (int e = 0; e < DIM * DIM; ++e) Ur[e] = HQ_LDG(&U[e]);
+  }
+
+  HQ_NOUNROLL
+  for (uint32_t it = 0; it < niter; ++it) {
+    const uint32_t sb = swz(ut | scatter_bits(it, g.q, tb, nq));
+    double2 in[DIM];
+    HQ_UNROLL
+    for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xoff<KK>(m, s)];
+    if (KK <= 1) {
+      HQ_UNROLL
+      for (int i = 0; i < DIM; ++i) {
+        double ar = 0., ai = 0.;
+        HQ_UNROLL
+        for (int j = 0; j < DIM; ++j) cmac(ar, ai, Ur[i * DIM + j].x, Ur[i * DIM + j].y, in[j].x, in[j].y);
+        tile[sb ^ xoff<KK>(i, s)] = make_double2(ar, ai);
+      }
+    } else {
+      HQ_NOUNROLL
+      for (int i = 0; i < DIM; ++i) {
+        double ar = 0., ai = 0.;
+        const double2* row = U + i * DIM;
+        HQ_UNROLL
+        for (int j = 0; j < DIM; ++j) {
+          const double2 u = HQ_LDG(&row[j]);
+          cmac(ar, ai, u.x, u.y, in[j].x, in[j].y);
+        }
+        tile[sb ^ xoff<KK>(uint32_t(i), s)] = make_double2(ar, ai);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// two-phase path for k >= 5 (amplitude granularity, any precision).  A round handles
+// HQ_THREADS * HQ_BIG_ROWS / 2^k whole groups: in phase A every thread accumulates
+// HQ_BIG_ROWS output rows of one group from shared memory into registers, the CTA
+// synchronises, and in phase B the rows are written back.  Lanes of a warp share the row
+// block (so the matrix loads are warp-uniform) and differ in the group.
+// The matrix is stored column-major: Ut[j * dim + i] = U[i][j].
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct BigAcc {
+  T re[HQ_BIG_ROWS], im[HQ_BIG_ROWS];
+  uint32_t base;    // local amplitude index of the group (zeros at the target bits)
+  uint32_t row0;
+  bool active;
+};
+
+template <typename T>
+HQ_DEV uint32_t amp_slot(uint32_t a) {   // local amplitude index -> index into a Cplx view of the tile
+  const int V = Traits<T>::V;
+  return (swz(a >> V) << V) | (a & ((1u << V) - 1u));
+}
+
+HQ_DEV int big_rounds(int T, int k) {
+  // groups in the tile / groups per round
+  const int groups_log2 = T - k;
+  const int per_round_log2 = HQ_THREADS_LOG2 + 3 - k;   // log2(HQ_THREADS * HQ_BIG_ROWS / 2^k)
+  const int r = groups_log2 - per_round_log2;
+  return r > 0 ? (1 << r) : 1;
+}
+
+template <typename T>
+HQ_DEV void gate_big_phaseA(const typename Traits<T>::Cplx* tile, const HqGateDesc& g,
+                            const typename Traits<T>::Cplx* __restrict__ Ut, int Tbits, int tid,
+                            int round, BigAcc<T>& acc) {
+  const int k = int(g.k);
+  const uint32_t dim = 1u << k;
+  const int groups_log2 = Tbits - k;
+  int per_round_log2 = HQ_THREADS_LOG2 + 3 - k;
+  if (per_round_log2 > groups_log2) per_round_log2 = groups_log2;
+  const uint32_t gl = uint32_t(tid) & ((1u << per_round_log2) - 1u);
+  const uint32_t rb = uint32_t(tid) >> per_round_log2;     // row block
+  acc.active = (rb * HQ_BIG_ROWS) < dim;
+  if (!acc.active) return;
+  const uint32_t grp = (uint32_t(round) << per_round_log2) | gl;
+  acc.base = scatter_bits(grp, g.q, 0, groups_log2);
+  acc.row0 = rb * HQ_BIG_ROWS;
+  HQ_UNROLL
+  for (int r = 0; r < HQ_BIG_ROWS; ++r) { acc.re[r] = T(0); acc.im[r] = T(0); }
+  HQ_NOUNROLL
+  for (uint32_t j = 0; j < dim; ++j) {
+    const uint32_t a = acc.base | uint32_t(deposit(j, g.tpos, k));
+    const typename Traits<T>::Cplx x = tile[amp_slot<T>(a)];
+    const typename Traits<T>::Cplx* col = Ut + size_t(j) * dim + acc.row0;
+    HQ_UNROLL
+    for (int r = 0; r < HQ_BIG_ROWS; ++r) {
+      const typename Traits<T>::Cplx u = HQ_LDG(&col[r]);
+      cmac(acc.re[r], acc.im[r], u.x, u.y, x.x, x.y);
+    }
+  }
+}
+
+template <typename T>
+HQ_DEV void gate_big_phaseB(typename Traits<T>::Cplx* tile, const HqGateDesc& g,
+                            const BigAcc<T>& acc) {
+  if (!acc.active) return;
+  const int k = int(g.k);
+  HQ_UNROLL
+  for (int r = 0; r < HQ_BIG_ROWS; ++r) {
+    const uint32_t a = acc.base | uint32_t(deposit(acc.row0 + r, g.tpos, k));
+    typename Traits<T>::Cplx o;
+    o.x = acc.re[r];
+    o.y = acc.im[r];
+    tile[amp_slot<T>(a)] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// dispatch of one register-path gate
+// ---------------------------------------------------------------------------------------
+// MAXK prunes the switch so that a pass made of small gates only is compiled with few
+// registers (the kernel is instantiated per gate class, see hq_kernels.cu).
+template <int MAXK>
+HQ_DEV void gate_small_dispatch(float4* tile, const HqGateDesc& g, const unsigned char* prog,
+                                int Tu, int tid) {
+  const float2* U = reinterpret_cast<const float2*>(prog + g.mat_off);
+  const bool low = g.tpos[0] == 0;
+  if (!low) {
+    switch (g.k) {
+      case 1: gate_small_f32<1>(tile, g, U, Tu, tid); break;
+      case 2: gate_small_f32<2>(tile, g, U, Tu, tid); break;
+      case 3: if (MAXK >= 3) gate_small_f32<3>(tile, g, U, Tu, tid); break;
+      case 4: if (MAXK >= 4) gate_small_f32<4>(tile, g, U, Tu, tid); break;
+      default: break;
+    }
+  } else {
+    switch (g.k) {
+      case 1: gate_small_f32_low<0>(tile, g, U, Tu, tid); break;
+      case 2: gate_small_f32_low<1>(tile, g, U, Tu, tid); break;
+      case 3: if (MAXK >= 3) gate_small_f32_low<2>(tile, g, U, Tu, tid); break;
+      case 4: if (MAXK >= 4) gate_small_f32_low<3>(tile, g, U, Tu, tid); break;
+      default: break;
+    }
+  }
+}
+
+template <int MAXK>
+HQ_DEV void gate_small_dispatch(double2* tile, const HqGateDesc& g, const unsigned char* prog,
+                                int Tu, int tid) {
+  const double2* U = reinterpret_cast<const double2*>(prog + g.mat_off);
+  switch (g.k) {
+    case 1: gate_small_f64<1>(tile, g, U, Tu, tid); break;
+    case 2: gate_small_f64<2>(tile, g, U, Tu, tid); break;
+    case 3: if (MAXK >= 3) gate_small_f64<3>(tile, g, U, Tu, tid); break;
+    case 4: if (MAXK >= 4) gate_small_f64<4>(tile, g, U, Tu, tid); break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tile fill / drain address math (the copies themselves are in the kernel / the emulator)
+// ---------------------------------------------------------------------------------------
+// local unit c of tile -> global unit index, given the tile's first unit and the run table.
+// run_off[r] = offset (in units) of run r from the tile's first unit.
+HQ_DEV uint64_t unit_global(uint32_t c, uint64_t base_unit, const uint64_t* run_off, int Lu) {
+  return base_unit + run_off[c >> Lu] + (c & ((1u << Lu) - 1u));
+}
+
+HQ_DEV float4 make_unit(const float2* a) { return make_float4(a[0].x, a[0].y, a[1].x, a[1].y); }
+HQ_DEV double2 make_unit(const double2* a) { return a[0]; }
+
+// Permuted drain: value of local amplitude j after the in-tile bit permutation.
+HQ_DEV uint32_t perm_src(uint32_t j, const uint8_t* perm, int Tbits) {
+  uint32_t y = 0;
+  for (int i = 0; i < Tbits; ++i) y |= ((j >> i) & 1u) << perm[i];
+  return y;
+}
+
+}  // namespace hq

@@ -1,0 +1,281 @@
+"""``simulate(circuit, initial_state, optimize='evolution', ...)`` -- host-side mirror of the
+reference entry point for the evolution path
+(/root/reference/hybridq/circuit/simulation/simulation.py:59 ``simulate`` and :372
+``_simulate_evolution``, hybridq branch :464-678), driving the device-resident C ABI.
+
+Same argument names and meaning, same errors for the same misuse, same return values
+(final state as a complex ndarray of shape ``(2,)*n``, optionally ``(state, info)`` with
+``info['runtime (s)']`` timing the gate loop only, :519/:666/:678).  What differs is where the
+state lives: it is uploaded once, every gate runs as part of a fused tile pass on the GPU and
+the result is downloaded once.  No per-gate low-bit permutation (:559-630) ever happens -- the
+kernels take any target bit -- and there is no split->complex pass at the end (:669-675).
+
+Gate objects are duck-typed on the part of the reference Gate API the hot loop uses
+(``gate.qubits``, ``gate.matrix()``, and ``gate.apply(psi, order)`` for FunctionalGates,
+:525-554, :633-637), so reference ``Gate``/``Circuit`` objects work unchanged when
+``hybridq`` is importable, and :class:`hybridq_b200.circuits.GateApply` works without it.
+When ``hybridq`` is importable its own pre-pass (``flatten``, ``simplify``, ``compress``,
+``to_matrix_gate``; circuit/utils.py) is used as is -- it is host-side graph rewriting and
+out of scope here.
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Iterable, Sequence
+from warnings import warn
+
+import numpy as np
+
+from ._lib import PlanOptions
+from .state import DeviceState, Plan
+
+
+def _try_hybridq():
+    try:
+        import hybridq.circuit as hc           # noqa: F401
+        import hybridq.circuit.utils as hu     # noqa: F401
+        import hybridq.gate.property as pr     # noqa: F401
+        return hc, hu, pr
+    except Exception:
+        return None
+
+
+def _sorted_qubits(qubits: Iterable) -> list:
+    """Sorted list of heterogeneous qubit labels; mirrors hybridq.utils.sort
+    (/root/reference/hybridq/utils/utils.py:283): plain ordering when the labels are
+    comparable, otherwise ordered by (type name, value)."""
+    qs = list(qubits)
+    try:
+        return sorted(qs)
+    except TypeError:
+        return sorted(qs, key=lambda x: (type(x).__name__, str(x)) if not isinstance(x, tuple)
+                      else ("tuple", tuple(str(y) for y in x)))
+
+
+def _is_functional(gate) -> bool:
+    """FunctionalGate = has ``apply(psi, order)`` and does not provide a matrix
+    (reference: isinstance(gate, pr.FunctionalGate), simulation.py:525)."""
+    hq = _try_hybridq()
+    if hq is not None and isinstance(gate, hq[2].FunctionalGate):
+        return True
+    prov = getattr(gate, "provides", None)
+    if callable(prov):
+        try:
+            if prov(["qubits", "matrix"]):
+                return False
+        except Exception:
+            pass
+    return callable(getattr(gate, "apply", None)) and not callable(getattr(gate, "matrix", None))
+
+
+def _flatten(circuit) -> list:
+    out = []
+    for g in circuit:
+        if hasattr(g, "qubits") and (callable(getattr(g, "matrix", None)) or callable(getattr(g, "apply", None))):
+            out.append(g)
+        elif hasattr(g, "__iter__"):
+            out.extend(_flatten(g))
+        else:
+            raise RuntimeError(f"'{g}' not supported")
+    return out
+
+
+def simulate(circuit,
+             initial_state: Any = None,
+             final_state: Any = None,
+             optimize: Any = "evolution",
+             backend: Any = "numpy",
+             complex_type: Any = "complex64",
+             tensor_only: bool = False,
+             simplify: Any = True,
+             remove_id_gates: bool = True,
+             use_mpi: bool | None = None,
+             atol: float = 1e-8,
+             verbose: bool = False,
+             **kwargs):
+    """Evolve `initial_state` through `circuit` on the GPU.  See the module docstring.
+
+    Extra keyword arguments (all optional): ``compress`` (int or dict, as in the reference;
+    default 0 here because gate fusion happens inside the kernel passes), ``max_largest_intermediate``,
+    ``return_info``, ``return_numpy_array`` (False returns the :class:`DeviceState`),
+    ``plan_options`` (:class:`PlanOptions`), ``device``.
+    """
+    if not (isinstance(optimize, str) and "evolution" in optimize):
+        raise NotImplementedError(
+            "hybridq_b200 implements optimize='evolution' only; use the reference for tensor-network "
+            "contraction.")
+    if tensor_only:
+        raise ValueError(f"'tensor_only' is not support for optimize={optimize}")
+    sub = "-".join(optimize.split("-")[1:]) or "hybridq"
+    if sub != "hybridq":
+        raise NotImplementedError("only optimize='evolution' / 'evolution-hybridq' run on the GPU core")
+
+    kwargs.setdefault("allow_sampling", False)
+    kwargs.setdefault("sampling_seed", None)
+    kwargs.setdefault("compress", 0)
+    kwargs.setdefault("max_largest_intermediate", None)
+    kwargs.setdefault("return_info", False)
+    kwargs.setdefault("return_numpy_array", True)
+    kwargs.setdefault("plan_options", None)
+    kwargs.setdefault("device", None)
+
+    hq = _try_hybridq()
+    is_ref_circuit = False
+    if hq is not None:
+        hc, hu, pr = hq
+        try:
+            circuit = hc.Circuit(circuit)
+            is_ref_circuit = True
+        except Exception:
+            is_ref_circuit = False
+
+    t_pre = time.perf_counter()
+    if is_ref_circuit:
+        # the reference's own host pre-pass, used as is (simulation.py:232-305, :436-454)
+        circuit = hu.flatten(circuit)
+        if kwargs["sampling_seed"] is not None:
+            _st = np.random.get_state()
+            np.random.seed(int(kwargs["sampling_seed"]))
+        circuit = hc.Circuit(g.sample() if isinstance(g, pr.StochasticGate) and kwargs["allow_sampling"] else g
+                             for g in circuit)
+        if kwargs["sampling_seed"] is not None:
+            np.random.set_state(_st)
+        qubits = circuit.all_qubits()
+        if remove_id_gates:
+            circuit = hc.Circuit(g for g in circuit if g.name != "I")
+        if simplify:
+            circuit = hu.simplify(circuit, remove_id_gates=remove_id_gates, atol=atol, verbose=verbose,
+                                  **(simplify if isinstance(simplify, dict) else {}))
+        if circuit.all_qubits() != qubits:
+            raise ValueError("Active qubits have changed after simplification. Forcing stop.")
+        comp = kwargs["compress"]
+        max_nq = comp["max_n_qubits"] if isinstance(comp, dict) else comp
+        if max_nq:
+            groups = hu.compress(circuit, max_nq, verbose=verbose, skip_compression=[pr.FunctionalGate],
+                                 **({k: v for k, v in comp.items() if k != "max_n_qubits"}
+                                    if isinstance(comp, dict) else {}))
+            circuit = hc.Circuit(g for c in (c if any(isinstance(g, pr.FunctionalGate) for g in c)
+                                             else [hu.to_matrix_gate(c, complex_type=complex_type)]
+                                             for c in groups) for g in c)
+        gates = list(circuit)
+    else:
+        gates = _flatten(circuit)
+        if remove_id_gates:
+            gates = [g for g in gates if getattr(g, "name", None) != "I"]
+        qubits = _sorted_qubits({q for g in gates for q in g.qubits})
+    n_qubits = len(qubits)
+
+    # initial / final state checks (simulation.py:261-286, :415-426)
+    def _prepare(state):
+        if isinstance(state, str):
+            if len(state) == 1:
+                state = state * n_qubits
+            if len(state) != n_qubits:
+                raise ValueError("Wrong number of qubits for initial/final state.")
+            if set(state).difference("+-01"):
+                raise ValueError(f"Symbols {set(state).difference('+-01')} are not allowed.")
+            return state
+        state = np.asarray(state)
+        if any(x != 2 for x in state.shape):
+            raise ValueError("Only qubits of dimension 2 are supported.")
+        if state.ndim != n_qubits:
+            raise ValueError("Wrong number of qubits for initial/final state.")
+        return state
+
+    initial_state = None if initial_state is None else _prepare(initial_state)
+    if final_state is not None:
+        warn(f"'final_state' cannot be specified in optimize='{optimize}'. Ignoring 'final_state'.")
+    if initial_state is None:
+        raise ValueError("'initial_state' must be specified for optimize='evolution'.")
+    if kwargs["max_largest_intermediate"] is not None and 2 ** n_qubits > kwargs["max_largest_intermediate"]:
+        raise MemoryError("Memory for the given number of qubits exceeds the 'max_largest_intermediate'.")
+
+    complex_type = np.dtype(complex_type)
+    if complex_type not in (np.dtype("complex64"), np.dtype("complex128")):
+        warn("optimize=evolution-hybridq only support ['complex64', 'complex128']. Using 'complex64'.")
+        complex_type = np.dtype("complex64")
+    if n_qubits < 1:
+        raise ValueError("empty circuit")
+
+    # qubit -> index bit, first sorted qubit = most significant bit (simulation.py:512-513)
+    qmap = {q: n_qubits - 1 - i for i, q in enumerate(qubits)}
+
+    # split the gate stream at FunctionalGates; everything else becomes (U, pos)
+    segments: list = []
+    cur: list = []
+    for g in gates:
+        if _is_functional(g):
+            if cur:
+                segments.append(("gates", cur))
+                cur = []
+            segments.append(("functional", g))
+        elif callable(getattr(g, "matrix", None)) and hasattr(g, "qubits"):
+            U = np.asarray(g.matrix(), dtype=complex_type, order="C")
+            pos = [qmap[q] for q in reversed(tuple(g.qubits))]
+            cur.append((U, pos))
+        else:
+            raise RuntimeError(f"'{g}' not supported")
+    if cur:
+        segments.append(("gates", cur))
+    t_pre = time.perf_counter() - t_pre
+
+    t_plan = time.perf_counter()
+    opts: PlanOptions | None = kwargs["plan_options"]
+    plans = [(kind, Plan(payload, n_qubits, complex_type, opts) if kind == "gates" else payload)
+             for kind, payload in segments]
+    t_plan = time.perf_counter() - t_plan
+
+    state = DeviceState(n_qubits, complex_type, device=kwargs["device"])
+    t_up = time.perf_counter()
+    if isinstance(initial_state, str):
+        state.init_product(initial_state)
+        state.sync()
+    else:
+        state.upload(initial_state.reshape(-1))
+    t_up = time.perf_counter() - t_up
+
+    # ---- the gate loop (this is what 'runtime (s)' times, as in the reference) ----
+    t0 = time.perf_counter()
+    n_passes = 0
+    n_gate_applies = 0
+    for kind, payload in plans:
+        if kind == "gates":
+            payload.run(state)
+            n_passes += payload.n_passes
+            n_gate_applies += payload.n_gates
+        else:
+            _apply_functional(payload, state, qmap)
+    state.sync()
+    runtime = time.perf_counter() - t0
+
+    info = {"runtime (s)": runtime, "pre-pass (s)": t_pre, "plan (s)": t_plan, "upload (s)": t_up,
+            "n_gate_applies": n_gate_applies, "n_passes": n_passes, "n_qubits": n_qubits}
+    if kwargs["return_numpy_array"]:
+        t_down = time.perf_counter()
+        psi = state.download().reshape((2,) * n_qubits)
+        info["download (s)"] = time.perf_counter() - t_down
+    else:
+        psi = state
+    return (psi, info) if kwargs["return_info"] else psi
+
+
+def _apply_functional(gate, state: DeviceState, qmap: dict) -> None:
+    """FunctionalGate contract of the reference (simulation.py:525-554): the gate receives
+    the state as a real array of shape (2,)+(2,)*n (re/im planes) plus the qubit order and
+    returns (new_psi, new_order).  With a device-resident state this is a D2H/H2D round
+    trip around arbitrary Python."""
+    n = state.n_qubits
+    order = tuple(q for q, _ in sorted(qmap.items(), key=lambda x: x[1])[::-1])
+    psi = state.download()
+    ft = np.float32 if state.complex_type == np.complex64 else np.float64
+    planes = np.empty((2,) + (2,) * n, dtype=ft)
+    planes[0] = psi.real.reshape((2,) * n)
+    planes[1] = psi.imag.reshape((2,) * n)
+    new_psi, new_order = gate.apply(psi=planes, order=order)
+    if any(x != y for x, y in zip(order, new_order)):
+        raise RuntimeError("'order' has changed.")
+    new_psi = np.asarray(new_psi)
+    out = np.empty(2 ** n, dtype=state.complex_type)
+    out.real = new_psi[0].reshape(-1)
+    out.imag = new_psi[1].reshape(-1)
+    state.upload(out)

@@ -1,0 +1,206 @@
+"""Device-resident state vector and circuit plans (thin Python over the C ABI).
+
+The state is ONE interleaved-complex array of 2^n amplitudes in HBM (a torch tensor is
+used purely as the allocation / stream / NCCL handle; every operation on it goes through
+libhybridq_b200.so with raw pointers).  This replaces the host-side split-plane buffer the
+reference allocates per simulation (/root/reference/hybridq/circuit/simulation/simulation.py:491-509)
+and makes its final ``to_complex`` pass (:669-675) unnecessary.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, PlanOptions
+
+
+def _stream_handle(stream=None) -> ctypes.c_void_p:
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _torch_ctype(complex_type):
+    import torch
+    return torch.complex64 if np.dtype(complex_type) == np.complex64 else torch.complex128
+
+
+class Plan:
+    """A circuit compiled into tile passes (hq_plan_*).  `gates` = [(U, pos), ...] with
+    LSB-first index-bit positions, U a 2^k x 2^k array (row-major)."""
+
+    def __init__(self, gates: Sequence, n_qubits: int, complex_type="complex64",
+                 options: PlanOptions | None = None):
+        self.n_qubits = int(n_qubits)
+        self.complex_type = np.dtype(complex_type)
+        self.dtype = _lib.dtype_code(complex_type)
+        ks = np.array([len(p) for _, p in gates], dtype=np.uint32)
+        pos = (np.concatenate([np.asarray(p, dtype=np.uint32).reshape(-1) for _, p in gates])
+               if len(gates) else np.zeros(0, np.uint32))
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        mats = []
+        for (U, p) in gates:
+            U = np.asarray(U, dtype=np.complex128)
+            if U.shape != (2 ** len(p), 2 ** len(p)):
+                raise ValueError(f"matrix of shape {U.shape} does not match {len(p)} positions")
+            mats.append(np.ascontiguousarray(U).reshape(-1))
+        flat = (np.concatenate(mats) if mats else np.zeros(0, np.complex128)).view(np.float64)
+        flat = np.ascontiguousarray(flat)
+        self.options = options or PlanOptions()
+        self._h = lib.hq_plan_create(self.dtype, self.n_qubits, len(gates),
+                                     ks.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                     pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                     flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                     ctypes.byref(self.options))
+        if not self._h:
+            raise _lib.HybridQB200Error(f"hq_plan_create failed: {_lib.last_error()}")
+        self.n_gates = lib.hq_plan_num_gates(self._h)
+        self.n_passes = lib.hq_plan_num_passes(self._h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.hq_plan_destroy(h)
+            self._h = None
+
+    def pass_info(self, p: int) -> dict:
+        out = (ctypes.c_uint32 * 32)()
+        check(lib.hq_plan_pass_info(self._h, p, out, 32), "hq_plan_pass_info")
+        ng = out[2]
+        ids = (ctypes.c_uint32 * max(1, ng))()
+        check(lib.hq_plan_pass_gates(self._h, p, ids, max(1, ng)), "hq_plan_pass_gates")
+        return {"tile_bits": out[0], "n_high": out[1], "n_gates": ng, "has_perm": out[3],
+                "high_pos": [out[4 + i] for i in range(out[1])], "gate_ids": [ids[i] for i in range(ng)]}
+
+    def run(self, state: "DeviceState", first: int | None = None, last: int | None = None, stream=None):
+        if state.n_qubits != self.n_qubits or state.dtype != self.dtype:
+            raise ValueError("plan and state disagree on size or precision")
+        if first is None and last is None:
+            check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream)), "hq_plan_run")
+        else:
+            check(lib.hq_plan_run_range(self._h, state.ptr, first or 0,
+                                        self.n_passes if last is None else last,
+                                        _stream_handle(stream)), "hq_plan_run_range")
+
+
+class DeviceState:
+    def __init__(self, n_qubits: int, complex_type="complex64", device: int | None = None, tensor=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.HybridQB200Error("hybridq_b200 needs a CUDA device (no CPU fallback)")
+        self.n_qubits = int(n_qubits)
+        self.complex_type = np.dtype(complex_type)
+        self.dtype = _lib.dtype_code(complex_type)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        if tensor is None:
+            with torch.cuda.device(self.device):
+                tensor = torch.empty(2 ** self.n_qubits, dtype=_torch_ctype(complex_type),
+                                     device=f"cuda:{self.device}")
+        self.tensor = tensor
+        self.n_amps = 2 ** self.n_qubits
+        self.nbytes = self.n_amps * self.complex_type.itemsize
+
+    @property
+    def ptr(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(self.tensor.data_ptr())
+
+    # -- transfers ------------------------------------------------------------------
+    def upload(self, psi: np.ndarray, stream=None, sync: bool = True) -> "DeviceState":
+        psi = np.asarray(psi)
+        if psi.size != self.n_amps:
+            raise ValueError("wrong number of amplitudes")
+        if psi.dtype != self.complex_type or not psi.flags.c_contiguous:
+            psi = np.ascontiguousarray(psi, dtype=self.complex_type)
+        s = _stream_handle(stream)
+        check(lib.hq_memcpy_h2d(self.ptr, ctypes.c_void_p(psi.ctypes.data), self.nbytes, s), "h2d")
+        if sync:
+            check(lib.hq_stream_sync(s), "sync")
+        return self
+
+    def download(self, out: np.ndarray | None = None, stream=None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.n_amps, dtype=self.complex_type)
+        if out.size != self.n_amps or out.dtype != self.complex_type or not out.flags.c_contiguous:
+            raise ValueError("bad output array")
+        s = _stream_handle(stream)
+        check(lib.hq_memcpy_d2h(ctypes.c_void_p(out.ctypes.data), self.ptr, self.nbytes, s), "d2h")
+        check(lib.hq_stream_sync(s), "sync")
+        return out
+
+    def sync(self, stream=None) -> None:
+        check(lib.hq_stream_sync(_stream_handle(stream)), "sync")
+
+    # -- preparation / reductions -----------------------------------------------------
+    def init_product(self, spec: str, stream=None) -> "DeviceState":
+        if len(spec) == 1:
+            spec = spec * self.n_qubits
+        check(lib.hq_init_product_dev(self.ptr, self.dtype, self.n_qubits, spec.encode(),
+                                      _stream_handle(stream)), "hq_init_product_dev")
+        return self
+
+    def init_random(self, seed: int = 0, index_offset: int = 0, scale: float = 0.0, stream=None):
+        check(lib.hq_init_random_dev(self.ptr, self.dtype, self.n_qubits, seed, index_offset, scale,
+                                     _stream_handle(stream)), "hq_init_random_dev")
+        return self
+
+    def norm2(self, stream=None) -> float:
+        r = ctypes.c_double()
+        check(lib.hq_norm2_dev(self.ptr, self.dtype, self.n_amps, ctypes.byref(r), _stream_handle(stream)),
+              "hq_norm2_dev")
+        return r.value
+
+    def vdot(self, other: "DeviceState", stream=None) -> complex:
+        """<self|other> = sum conj(self) * other."""
+        r = (ctypes.c_double * 2)()
+        check(lib.hq_vdot_dev(self.ptr, other.ptr, self.dtype, self.n_amps, r, _stream_handle(stream)),
+              "hq_vdot_dev")
+        return complex(r[0], r[1])
+
+    def scale(self, factor: float, stream=None):
+        check(lib.hq_scale_dev(self.ptr, self.dtype, self.n_amps, float(factor), _stream_handle(stream)),
+              "hq_scale_dev")
+        return self
+
+    def copy(self) -> "DeviceState":
+        return DeviceState(self.n_qubits, self.complex_type, self.device, tensor=self.tensor.clone())
+
+    # -- gates -------------------------------------------------------------------------
+    def apply(self, U: np.ndarray, pos: Sequence[int], stream=None, direct: bool = False):
+        """One gate-apply (hq_apply_U_dev): pos[i] = index bit of matrix bit i, any bits."""
+        U = np.ascontiguousarray(U, dtype=self.complex_type)
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        fn = lib.hq_apply_U_direct_dev if direct else lib.hq_apply_U_dev
+        check(fn(self.ptr, self.dtype, self.n_qubits, ctypes.c_void_p(U.ctypes.data),
+                 pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos), _stream_handle(stream)),
+              "hq_apply_U_dev")
+        return self
+
+    def swap(self, pos: Sequence[int], stream=None):
+        """In-place permutation of the low len(pos) index bits (hq_swap_dev)."""
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        check(lib.hq_swap_dev(self.ptr, self.dtype, self.n_qubits,
+                              pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos),
+                              _stream_handle(stream)), "hq_swap_dev")
+        return self
+
+    def permute_bits(self, perm: Sequence[int], options: PlanOptions | None = None, stream=None):
+        """new index bit i <- old index bit perm[i] for every i < n (in place)."""
+        perm = np.ascontiguousarray(perm, dtype=np.uint32)
+        if len(perm) != self.n_qubits:
+            raise ValueError("perm must list every bit")
+        h = lib.hq_plan_create_bitperm(self.dtype, self.n_qubits,
+                                       perm.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                       ctypes.byref(options or PlanOptions()))
+        if not h:
+            raise _lib.HybridQB200Error(f"hq_plan_create_bitperm failed: {_lib.last_error()}")
+        try:
+            check(lib.hq_plan_run(h, self.ptr, _stream_handle(stream)), "hq_plan_run")
+            check(lib.hq_stream_sync(_stream_handle(stream)), "sync")
+        finally:
+            lib.hq_plan_destroy(h)
+        return self

@@ -1,0 +1,161 @@
+/*
+ * hybridq_b200.h -- C ABI of libhybridq_b200.so, the B200-native (sm_100a) state-vector
+ * evolution core for HybridQ.
+ *
+ * Part 1 is the DROP-IN boundary: the exact eleven symbols the reference binds with
+ * ctypes from 'hybridq.so' and 'hybridq_swap.so' (the same library file is installed
+ * under both names).  Host pointers in, host pointers out, results
+ * visible in host memory on return, return code 0 = OK / 1 = rejected, never throws.
+ *
+ * Part 2 is the device-resident extension used by hybridq_b200.simulate(): the state
+ * stays in HBM across gates as ONE interleaved-complex array, circuits are planned once
+ * (gate fusion into tile passes) and run as a sequence of kernel launches on a stream.
+ *
+ * All functions return 0 on success unless stated otherwise; hq_last_error() gives a
+ * human-readable message for the calling thread's last failure.  No torch types, plain
+ * pointers and sizes only.  `stream` arguments are cudaStream_t passed as void* (NULL =
+ * default stream).  `dtype`: 0 = complex64 (float pairs), 1 = complex128 (double pairs).
+ */
+#ifndef HYBRIDQ_B200_H
+#define HYBRIDQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================
+ * Part 1 -- reference-compatible symbols
+ * =================================================================================== */
+
+/* Replaces get_log2_pack_size, /root/reference/include/python_U.cpp:129 (bound at
+ * hybridq/utils/dot.py:65-66).  The reference's host logic permutes index bits away
+ * whenever a gate touches a bit below this value (simulation.py:559) and treats 0 as
+ * "library missing" (simulation.py:393-394).  The GPU kernels have no pack, so this
+ * returns the smallest legal value, 1. */
+unsigned int get_log2_pack_size(void);
+
+/* Replace apply_U_float32/64, /root/reference/include/python_U.cpp:131-143 (bound at
+ * dot.py:69-78; called from simulation.py:640-646 and dot.py:305-307).
+ * In place on two host real planes re[2^n], im[2^n]; U = row-major 2^k x 2^k complex,
+ * interleaved; pos[i] = index bit (LSB 0) of matrix bit i.  Returns 1 -- and touches
+ * nothing -- if re or im is not 32-byte aligned (U.h:34-36) or any pos[i] is below
+ * get_log2_pack_size() (U.h:48-54) or >= n_qubits / duplicated; n_pos = 0 is a no-op
+ * (python_U.cpp:38-39).  Returns 2 on a CUDA failure (see hq_last_error). */
+int apply_U_float32(float* psi_re, float* psi_im, const float* U, const unsigned int* pos,
+                    unsigned int n_qubits, unsigned int n_pos);
+int apply_U_float64(double* psi_re, double* psi_im, const double* U, const unsigned int* pos,
+                    unsigned int n_qubits, unsigned int n_pos);
+
+/* Replace to_complex64/128, /root/reference/include/python_U.cpp:145-153 (bound at
+ * dot.py:81-89; called from simulation.py:669-674): out[2i] = re[i], out[2i+1] = im[i].
+ * `size` is 32-bit exactly as in the reference (python_U.cpp:115-116). */
+int to_complex64(float* psi_re, float* psi_im, float* psi, unsigned int size);
+int to_complex128(double* psi_re, double* psi_im, double* psi, unsigned int size);
+
+/* Replace swap_*, /root/reference/include/python_swap.cpp:70-98 (bound at
+ * hybridq/utils/transpose.py:42-58; called from simulation.py:623-630, :658-663,
+ * dot.py:291-317, transpose.py:148).  In place on a host array of 2^n_qubits elements:
+ * inside every aligned block of 2^n_pos elements new[j] = old[sigma(j)],
+ * sigma(j) = XOR_i bit_i(j) << pos[i]  (swap.h:28-33).  n_pos = 0 is a no-op. */
+int swap_float32(float* array, const unsigned int* pos, unsigned int n_qubits, unsigned int n_pos);
+int swap_float64(double* array, const unsigned int* pos, unsigned int n_qubits, unsigned int n_pos);
+int swap_int32(int* array, const unsigned int* pos, unsigned int n_qubits, unsigned int n_pos);
+int swap_int64(long* array, const unsigned int* pos, unsigned int n_qubits, unsigned int n_pos);
+int swap_uint32(unsigned int* array, const unsigned int* pos, unsigned int n_qubits, unsigned int n_pos);
+int swap_uint64(unsigned long* array, const unsigned int* pos, unsigned int n_qubits, unsigned int n_pos);
+
+/* ===================================================================================
+ * Part 2 -- device-resident extension (what `_simulate_evolution`'s hybridq branch,
+ * simulation.py:464-678, becomes when the state lives in HBM)
+ * =================================================================================== */
+
+int hq_version(void);
+const char* hq_last_error(void);
+int hq_device_count(int* count);
+int hq_set_device(int device);
+int hq_device_props(int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor);
+
+/* raw memory (replaces hybridq.utils.aligned.empty for the state, aligned_array.py:69-143) */
+int hq_malloc(void** dptr, size_t bytes);
+int hq_free(void* dptr);
+int hq_host_alloc(void** hptr, size_t bytes);      /* pinned */
+int hq_host_free(void* hptr);
+int hq_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+int hq_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+int hq_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int hq_stream_sync(void* stream);
+
+/* one gate on a device-resident interleaved state; any distinct pos in [0, n) incl. bit 0 */
+int hq_apply_U_dev(void* state, int dtype, unsigned int n_qubits, const void* U_host,
+                   const unsigned int* pos, unsigned int n_pos, void* stream);
+/* same, with the shared-memory-free kernel (k <= 3); for measurements */
+int hq_apply_U_direct_dev(void* state, int dtype, unsigned int n_qubits, const void* U_host,
+                          const unsigned int* pos, unsigned int n_pos, void* stream);
+
+/* In-place permutation of the low n_pos index bits of a device-resident interleaved state,
+ * same sigma convention as swap_* (replaces the pair of swap calls on the re and im planes,
+ * simulation.py:623-630). */
+int hq_swap_dev(void* state, int dtype, unsigned int n_qubits, const unsigned int* pos,
+                unsigned int n_pos, void* stream);
+
+/* split planes <-> interleaved, all pointers on the device */
+int hq_pack_dev(const void* re, const void* im, void* out, int dtype, uint64_t n_amps, void* stream);
+int hq_unpack_dev(const void* in, void* re, void* im, int dtype, uint64_t n_amps, void* stream);
+
+/* state preparation (prepare_state, hybridq/circuit/simulation/utils.py:40-156): spec is a
+ * string of n_qubits characters from "01+-", spec[0] = most significant index bit */
+int hq_init_product_dev(void* state, int dtype, unsigned int n_qubits, const char* spec, void* stream);
+/* seeded complex Gaussian, normalised to 1; amplitude i depends only on (seed, index_offset+i) */
+int hq_init_random_dev(void* state, int dtype, unsigned int n_qubits, uint64_t seed,
+                       uint64_t index_offset, double scale, void* stream);
+int hq_norm2_dev(const void* state, int dtype, uint64_t n_amps, double* result_host, void* stream);
+int hq_vdot_dev(const void* a, const void* b, int dtype, uint64_t n_amps, double* re_im_host, void* stream);
+int hq_scale_dev(void* state, int dtype, uint64_t n_amps, double factor, void* stream);
+
+/* ---- circuit plans: fuse a gate stream into tile passes once, run many times ---- */
+typedef struct hq_plan hq_plan;
+
+typedef struct hq_plan_options {
+  int tile_bits;            /* log2 amplitudes per tile; 0 = default (12 c64 / 11 c128) */
+  int min_run_bits;         /* smallest contiguous run the fuser may create; -1 = default */
+  int fuse;                 /* 0 = one pass per gate */
+  int max_gates_per_pass;   /* 0 = default */
+  int lookahead;            /* 0 = default */
+} hq_plan_options;
+
+/* gates: n_gates entries; ks[g] = number of target bits; pos_flat = concatenated positions;
+ * U_flat = concatenated row-major matrices, complex128 (double pairs) regardless of dtype */
+hq_plan* hq_plan_create(int dtype, unsigned int n_qubits, unsigned int n_gates,
+                        const unsigned int* ks, const unsigned int* pos_flat,
+                        const double* U_flat, const hq_plan_options* opts);
+/* plan made of permutation passes only: new index bit i <- old index bit perm[i], i < n_qubits */
+hq_plan* hq_plan_create_bitperm(int dtype, unsigned int n_qubits, const unsigned int* perm,
+                                const hq_plan_options* opts);
+void hq_plan_destroy(hq_plan* plan);
+int hq_plan_num_passes(const hq_plan* plan);
+int hq_plan_num_gates(const hq_plan* plan);
+/* per pass: tile_bits, n_high, n_gates, has_perm, high_pos[0..n_high) -> out[0..4+n_high) */
+int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len);
+/* gate ids (indices into the creation arrays) of a pass, in execution order */
+int hq_plan_pass_gates(const hq_plan* plan, int pass, unsigned int* out, int out_len);
+/* launch every pass on `stream` (asynchronous); the program is uploaded on first use */
+int hq_plan_run(hq_plan* plan, void* state, void* stream);
+/* launch passes [first, last) only */
+int hq_plan_run_range(hq_plan* plan, void* state, int first, int last, void* stream);
+
+/* measurement knobs of the tile kernel: nbuf = 1 (single-buffered tiles) or 2 (the next tile is
+ * prefetched while the current one is processed; default); ctas_per_sm = cap on resident CTAs
+ * per SM (0 = occupancy limit; default) */
+int hq_set_tuning(int nbuf, int ctas_per_sm);
+
+/* counters: kernels launched by this library in this process since the last reset */
+uint64_t hq_launch_count(void);
+void hq_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYBRIDQ_B200_H */

@@ -1,0 +1,31 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    return O
+
+
+@pytest.fixture(scope="session")
+def c_oracle(oracle):
+    return oracle.COracle()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    d = ROOT / "tests" / "golden"
+    return {p.stem: np.load(p, allow_pickle=False) for p in sorted(d.glob("*.npz"))}

@@ -1,0 +1,111 @@
+"""CPU model of the CUDA kernel phases (hq_tile.cuh compiled by g++, driven by hq_emu.cpp) and
+the planner, checked against the oracle.  No GPU involved; this only validates index math."""
+import numpy as np
+import pytest
+
+from helpers import Emu, golden_gates, lower, initial_from, product_state, TOL
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+def _rand_state(rng, n, ctype):
+    psi = (rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)).astype(ctype)
+    return (psi / np.linalg.norm(psi)).astype(ctype)
+
+
+def _rand_gate(rng, n, k):
+    U = (rng.standard_normal((2 ** k, 2 ** k)) + 1j * rng.standard_normal((2 ** k, 2 ** k))) / 2 ** (k / 2)
+    return U, rng.permutation(n)[:k]
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [3, 7, 11, 13])
+def test_random_circuits_vs_oracle(emu, oracle, c_oracle, ctype, n):
+    rng = np.random.default_rng(100 + n)
+    tol = 2e-5 if ctype == "complex64" else 1e-12
+    for trial in range(6):
+        psi = _rand_state(rng, n, ctype)
+        gates = [_rand_gate(rng, n, int(rng.integers(1, min(n, 7) + 1))) for _ in range(int(rng.integers(1, 14)))]
+        ref = oracle.evolve_oracle(psi, [(u.astype(ctype), p) for u, p in gates], c_oracle)
+        for opts in (None, (8, 2, 1, 0, 0), (8, 3, 0, 0, 0), (9, 1, 1, 4, 0), (13, 5, 1, 0, 0)):
+            out, n_pass, n_gates = emu.run(psi, gates, opts)
+            assert n_gates == len(gates)
+            assert np.abs(out - ref).max() < tol, (ctype, n, trial, opts)
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_every_k_every_low_bit(emu, oracle, c_oracle, ctype):
+    """k = 1..8 with targets including bit 0 (inside the 16-byte unit for complex64)."""
+    rng = np.random.default_rng(5)
+    n = 12
+    for k in range(1, 9):
+        for low in (True, False):
+            psi = _rand_state(rng, n, ctype)
+            pool = np.arange(1, n)
+            pos = list(rng.permutation(pool)[:k - 1]) + ([0] if low else [int(rng.permutation(pool)[-1])])
+            pos = [int(x) for x in rng.permutation(pos)]
+            if len(set(pos)) != k:
+                continue
+            U = _rand_gate(rng, n, k)[0]
+            ref = oracle.evolve_oracle(psi, [(U.astype(ctype), pos)], c_oracle)
+            for T in (10, 12):
+                out, _, _ = emu.run(psi, [(U, pos)], (T, 1, 0, 0, 0))
+                assert np.abs(out - ref).max() < (2e-5 if ctype == "complex64" else 1e-12), (k, low, T)
+
+
+def test_golden_circuits_through_emu(emu, golden):
+    z = golden["simulate"]
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"s{i}_ctype"])
+        gq, n = golden_gates(z, f"s{i}")
+        gates = lower(gq, n)
+        init = initial_from(z, f"s{i}_init", n, ctype)
+        psi0 = product_state(init, ctype) if isinstance(init, str) else init
+        out, n_pass, _ = emu.run(psi0.astype(ctype), gates, (9, 3, 1, 0, 0))
+        assert np.abs(out - z[f"s{i}_out"]).max() < 4 * TOL[ctype]
+        assert n_pass < len(gates)                    # fusion happened
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_bitperm(emu, oracle, ctype):
+    rng = np.random.default_rng(9)
+    n = 13
+    psi = _rand_state(rng, n, ctype)
+    for trial in range(10):
+        if trial % 2:
+            perm = rng.permutation(n)                          # needs several passes
+        else:
+            m = int(rng.integers(2, 9))
+            perm = np.concatenate([rng.permutation(m), np.arange(m, n)])
+        ref = oracle.numpy_swap(psi, perm)                     # new bit i <- old bit perm[i]
+        for opts in (None, (8, 2, 1, 0, 0), (10, 4, 1, 0, 0)):
+            out, n_pass = emu.bitperm(psi, perm, opts)
+            assert np.array_equal(out, ref), (trial, opts)     # pure data movement: bit-exact
+
+
+def test_planner_properties(emu):
+    """Every gate exactly once; gates sharing a bit keep their order; tiles fit."""
+    rng = np.random.default_rng(11)
+    for dtype, V in ((0, 1), (1, 0)):
+        for n in (14, 20, 30):
+            gates = [list(rng.permutation(n)[:int(rng.integers(1, 5))]) for _ in range(300)]
+            for opts in (None, (12, 5, 1, 0, 0), (13, 4, 1, 8, 0), (11, 5, 0, 0, 0)):
+                passes = emu.plan(dtype, n, gates, opts)
+                order = [g for p in passes for g in p["gate_ids"]]
+                assert sorted(order) == list(range(len(gates)))
+                when = {g: i for i, g in enumerate(order)}
+                for a in range(len(gates)):
+                    for b in range(a + 1, len(gates)):
+                        if set(gates[a]) & set(gates[b]):
+                            assert when[a] < when[b]
+                for p in passes:
+                    L = p["tile_bits"] - p["n_high"]
+                    assert L >= V and p["tile_bits"] <= min(n, 12 + V)
+                    for g in p["gate_ids"]:
+                        for bit in gates[g]:
+                            assert bit < L or bit in p["high_pos"]
+                if opts and opts[2] == 0:
+                    assert all(p["n_gates"] == 1 for p in passes)

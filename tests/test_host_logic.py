@@ -1,0 +1,57 @@
+"""Host-side logic that needs neither the GPU nor the oracle."""
+import numpy as np
+import pytest
+
+from hybridq_b200.circuits import (GateApply, matching_circuit, ksweep_circuit, sharded_circuit,
+                                   to_positions)
+
+
+def test_matching_circuit_is_seeded_and_well_formed():
+    a = matching_circuit(20, depth=20, seed=20)
+    b = matching_circuit(20, depth=20, seed=20)
+    assert len(a) == len(b) and 250 < len(a) < 350
+    for g, h in zip(a, b):
+        assert g.qubits == h.qubits and np.array_equal(g.U, h.U)
+        d = 2 ** len(g.qubits)
+        assert np.allclose(g.U @ g.U.conj().T, np.eye(d), atol=1e-12)
+
+
+def test_positions_follow_reference_convention():
+    # first sorted qubit is the most significant bit; gate.qubits[0] is the matrix MSB
+    g = GateApply(np.eye(4), ("a", "c"))
+    h = GateApply(np.eye(2), ("b",))
+    lowered, n = to_positions([g, h])
+    assert n == 3
+    assert lowered[0][1] == [0, 2]      # reversed(('a','c')) -> c is bit 0, a is bit 2
+    assert lowered[1][1] == [1]
+
+
+def test_sharded_circuit_fraction():
+    gates = sharded_circuit(30, 3, depth=20, frac_global=0.2, seed=36)
+    frac = np.mean([any(q < 3 for q in g.qubits) for g in gates])
+    assert 0.1 < frac < 0.3
+
+
+def test_ksweep():
+    for k in range(1, 7):
+        gs = ksweep_circuit(16, k, n_gates=5)
+        assert all(len(set(g.qubits)) == k and g.U.shape == (2 ** k, 2 ** k) for g in gs)
+
+
+def test_simulate_argument_errors_mirror_the_reference():
+    import hybridq_b200 as hb
+    gates = matching_circuit(12, depth=1, seed=1)
+    with pytest.raises(ValueError, match="initial_state"):
+        hb.simulate(gates, initial_state=None)
+    with pytest.raises(ValueError, match="Wrong number of qubits"):
+        hb.simulate(gates, initial_state="000")
+    with pytest.raises(ValueError, match="not allowed"):
+        hb.simulate(gates, initial_state="x" * 12)
+    with pytest.raises(ValueError, match="dimension 2"):
+        hb.simulate(gates, initial_state=np.zeros((3,) * 12))
+    with pytest.raises(MemoryError):
+        hb.simulate(gates, initial_state="0", max_largest_intermediate=2 ** 10)
+    with pytest.raises(ValueError, match="tensor_only"):
+        hb.simulate(gates, initial_state="0", tensor_only=True)
+    with pytest.raises(NotImplementedError):
+        hb.simulate(gates, initial_state="0", optimize="tn")
