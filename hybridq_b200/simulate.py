@@ -98,7 +98,7 @@ def simulate(circuit,
     Extra keyword arguments (all optional): ``compress`` (int or dict, as in the reference;
     default 0 here because gate fusion happens inside the kernel passes), ``max_largest_intermediate``,
     ``return_info``, ``return_numpy_array`` (False returns the :class:`DeviceState`),
-    ``plan_options`` (:class:`PlanOptions`), ``device``.
+    ``plan_options`` (:class:`PlanOptions`), ``device``, ``out`` (preallocated, e.g. pinned, result array).
     """
     if not (isinstance(optimize, str) and "evolution" in optimize):
         raise NotImplementedError(
@@ -118,6 +118,7 @@ def simulate(circuit,
     kwargs.setdefault("return_numpy_array", True)
     kwargs.setdefault("plan_options", None)
     kwargs.setdefault("device", None)
+    kwargs.setdefault("out", None)           # optional (e.g. pinned) complex array receiving the result
 
     hq = _try_hybridq()
     is_ref_circuit = False
@@ -252,7 +253,8 @@ def simulate(circuit,
             "n_gate_applies": n_gate_applies, "n_passes": n_passes, "n_qubits": n_qubits}
     if kwargs["return_numpy_array"]:
         t_down = time.perf_counter()
-        psi = state.download().reshape((2,) * n_qubits)
+        out = kwargs["out"]
+        psi = state.download(out.reshape(-1) if out is not None else None).reshape((2,) * n_qubits)
         info["download (s)"] = time.perf_counter() - t_down
     else:
         psi = state

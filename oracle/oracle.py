@@ -148,9 +148,12 @@ def numpy_swap(a: np.ndarray, pos) -> np.ndarray:
 class RefCore:
     """ctypes binding of the reference core with the reference's own prototypes."""
 
-    def __init__(self, variant: str = "avx2"):
-        d = REFDIR / variant
-        self.variant = variant
+    def __init__(self, variant: str = "avx2", path: os.PathLike | None = None):
+        """`path`: directory holding hybridq.so / hybridq_swap.so; defaults to oracle/_ref/<variant>.
+        Any library exporting the reference's eleven symbols can be bound this way -- the GPU
+        tests bind this repo's drop-in copies to drive them exactly like the reference does."""
+        d = Path(path) if path is not None else REFDIR / variant
+        self.variant = variant if path is None else str(path)
         self.lib_u = ctypes.CDLL(str(d / "hybridq.so"))
         self.lib_s = ctypes.CDLL(str(d / "hybridq_swap.so"))
         self.lib_u.get_log2_pack_size.restype = ctypes.c_uint32

@@ -1,0 +1,273 @@
+"""GPU parity tests proper: everything goes through the C ABI of libhybridq_b200.so and is
+compared with the oracle / the golden vectors of the unmodified reference.
+Tolerances (BASELINE.json north_star): max-abs 1e-6 complex64, 1e-12 complex128."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import TOL, golden_gates, lower, initial_from, product_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hybridq_b200
+    return hybridq_b200
+
+
+def _rand_state(rng, n, ctype):
+    psi = (rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)).astype(ctype)
+    return (psi / np.linalg.norm(psi)).astype(ctype)
+
+
+def _haar(rng, k):
+    from hybridq_b200.circuits import haar_unitary
+    return haar_unitary(2 ** k, rng)
+
+
+# ------------------------------------------------------------------ Part 1: host-pointer ABI
+def test_host_abi_apply_u_golden(hb, oracle, golden):
+    z = golden["apply_u"]
+    lib = hb.lib
+    assert lib.get_log2_pack_size() == 1
+    for i in range(int(z["n_cases"])):
+        psi, U, pos, ref = z[f"c{i}_psi"], z[f"c{i}_U"], z[f"c{i}_pos"], z[f"c{i}_out"]
+        ctype = str(psi.dtype)
+        planes = oracle.split_state(psi, alignment=32)
+        ct = ctypes.c_float if ctype == "complex64" else ctypes.c_double
+        fn = lib.apply_U_float32 if ctype == "complex64" else lib.apply_U_float64
+        p = ctypes.POINTER(ct)
+        Uc = np.ascontiguousarray(U)
+        posc = np.ascontiguousarray(pos, dtype=np.uint32)
+        n = int(np.log2(psi.size))
+        rc = fn(planes[0].ctypes.data_as(p), planes[1].ctypes.data_as(p), Uc.ctypes.data_as(p),
+                posc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), n, len(posc))
+        assert rc == 0, hb._lib.last_error()
+        out = planes[0] + 1j * planes[1]
+        assert np.abs(out - ref).max() <= TOL[ctype], (i, len(pos))
+
+
+def test_host_abi_swap_and_to_complex_golden(hb, oracle, golden):
+    z = golden["swap"]
+    n = int(z["n"])
+    core = oracle.RefCore(path=hb.DROPIN_DIR)         # this repo's library under the reference's names
+    for i in range(int(z["n_cases"])):
+        dt = str(z[f"c{i}_dtype"])
+        a = (np.arange(2 ** n, dtype=np.int64) * 7 + 3).astype(dt)
+        assert core.swap(a, z[f"c{i}_pos"]) == 0
+        assert np.array_equal(a, z[f"c{i}_out"]), i       # bit-exact
+    rng = np.random.default_rng(0)
+    for ft in (np.float32, np.float64):
+        re = rng.standard_normal(5000).astype(ft)
+        im = rng.standard_normal(5000).astype(ft)
+        assert np.array_equal(core.to_complex(re, im), re + 1j * im)
+        assert np.array_equal(hb.to_complex(re, im), re + 1j * im)
+
+
+def test_reference_style_host_loop_over_the_dropin_library(hb, oracle, c_oracle, golden):
+    """Drive swap_* / apply_U_* / to_complex* in the order the reference's own host loop
+    would (simulation.py:522-675), on the golden circuits, with this library bound under the
+    reference's file names."""
+    core = oracle.RefCore(path=hb.DROPIN_DIR)
+    assert core.log2_pack_size == 1
+    z = golden["simulate"]
+    for i in (0, 2, 8, 9):
+        ctype = str(z[f"s{i}_ctype"])
+        gq, n = golden_gates(z, f"s{i}")
+        gates = [(U.astype(ctype), p) for U, p in lower(gq, n)]
+        init = initial_from(z, f"s{i}_init", n, ctype)
+        psi0 = product_state(init, ctype) if isinstance(init, str) else init
+        out = oracle.evolve_ref(psi0, gates, core)
+        assert np.abs(out - z[f"s{i}_out"]).max() <= 4 * TOL[ctype], i
+
+
+# ------------------------------------------------------------------ Part 2: device-resident ABI
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_device_apply_every_k_any_bits(hb, oracle, c_oracle, ctype):
+    rng = np.random.default_rng(21)
+    n = 15
+    for k in range(1, 9):
+        for variant in range(4):
+            psi = _rand_state(rng, n, ctype)
+            if variant == 0:
+                pos = list(range(k))                                   # lowest bits incl. bit 0
+            elif variant == 1:
+                pos = list(range(n - k, n))                            # highest bits
+            else:
+                pos = [int(x) for x in rng.permutation(n)[:k]]
+            pos = [int(x) for x in rng.permutation(pos)]
+            U = _haar(rng, k).astype(ctype)
+            planes = oracle.split_state(psi)
+            assert c_oracle.apply_U(planes[0], planes[1], U, pos) == 0
+            ref = c_oracle.to_complex(planes[0], planes[1])
+            st = hb.DeviceState(n, ctype).upload(psi)
+            out = st.apply(U, pos).download()
+            assert np.abs(out - ref).max() <= TOL[ctype], (k, pos)
+            if k <= 3:
+                out = hb.DeviceState(n, ctype).upload(psi).apply(U, pos, direct=True).download()
+                assert np.abs(out - ref).max() <= TOL[ctype], ("direct", k, pos)
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_plan_variants_vs_oracle(hb, oracle, c_oracle, ctype):
+    from hybridq_b200.circuits import matching_circuit, to_positions
+    rng = np.random.default_rng(22)
+    n = 18
+    gates = matching_circuit(n, depth=8, seed=18)
+    lowered, _ = to_positions(gates)
+    # add a few wide gates (k = 3..6) so every kernel class runs inside fused passes
+    for k in (3, 4, 5, 6):
+        lowered.insert(int(rng.integers(0, len(lowered))), (_haar(rng, k), [int(x) for x in rng.permutation(n)[:k]]))
+    psi = _rand_state(rng, n, ctype)
+    ref = oracle.evolve_oracle(psi, [(U.astype(ctype), p) for U, p in lowered], c_oracle)
+    try:
+        for nbuf in (1, 2):
+            hb.lib.hq_set_tuning(nbuf, 0)
+            for opts in (None, hb.PlanOptions(10, 3, 1, 0, 0), hb.PlanOptions(13, 5, 1, 0, 0),
+                         hb.PlanOptions(12, 5, 0, 0, 0), hb.PlanOptions(11, 1, 1, 3, 0)):
+                plan = hb.Plan(lowered, n, ctype, opts)
+                st = hb.DeviceState(n, ctype).upload(psi)
+                plan.run(st)
+                out = st.download()
+                assert plan.n_gates == len(lowered)
+                assert np.abs(out - ref).max() <= TOL[ctype], (nbuf, opts and opts.tile_bits)
+    finally:
+        hb.lib.hq_set_tuning(2, 0)
+
+
+def test_simulate_golden(hb, golden):
+    from hybridq_b200.circuits import GateApply
+    z = golden["simulate"]
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"s{i}_ctype"])
+        gq, n = golden_gates(z, f"s{i}")
+        gates = [GateApply(U, tuple(int(x) for x in q)) for U, q in gq]     # qubit label = sorted index
+        init = initial_from(z, f"s{i}_init", n, ctype)
+        init_arg = init if isinstance(init, str) else init.reshape((2,) * n)
+        out, info = hb.simulate(gates, initial_state=init_arg, complex_type=ctype, return_info=True)
+        assert out.shape == (2,) * n and out.dtype == np.dtype(ctype)
+        assert np.abs(out.reshape(-1) - z[f"s{i}_out"]).max() <= 4 * TOL[ctype], (i, str(z[f"s{i}_tag"]))
+        assert info["n_passes"] < info["n_gate_applies"]
+
+
+def test_dm_golden(hb, golden):
+    """Config 5 path: the lowered super-operator circuit (non-unitary 4x4 / 16x16 matrices)."""
+    from hybridq_b200.circuits import GateApply
+    z = golden["dm"]
+    n = int(z["n_super"])
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"m{i}_ctype"])
+        gates = [GateApply(z[f"m{i}_g{j}_U"], tuple(int(x) for x in z[f"m{i}_g{j}_q"]))
+                 for j in range(int(z[f"m{i}_ngates"]))]
+        init = z[f"m{i}_init"]
+        init_arg = str(init) if init.dtype.kind in "US" else init.astype(ctype).reshape((2,) * n)
+        out = hb.simulate(gates, initial_state=init_arg, complex_type=ctype)
+        assert np.abs(out.reshape(-1) - z[f"m{i}_out"]).max() <= TOL[ctype]
+        rho = out.reshape(2 ** (n // 2), 2 ** (n // 2))
+        assert abs(np.trace(rho) - 1) < 1e-5 and np.abs(rho - rho.conj().T).max() < 1e-5
+
+
+def test_dot_and_transpose_golden(hb, golden):
+    z = golden["dot"]
+    n = int(z["n"])
+    for i in range(int(z["n_cases"])):
+        psi, U, axes, ref = z[f"d{i}_psi"], z[f"d{i}_U"], z[f"d{i}_axes"], z[f"d{i}_out"]
+        ctype = str(psi.dtype)
+        out = hb.dot(U, psi.reshape((2,) * n), axes_b=axes)
+        assert np.abs(out.reshape(-1) - ref).max() <= TOL[ctype], i
+        planes = np.array([psi.real.reshape((2,) * n), psi.imag.reshape((2,) * n)])
+        out2 = hb.dot(U, planes, axes_b=axes, b_as_complex_array=True)
+        assert np.abs((out2[0] + 1j * out2[1]).reshape(-1) - ref).max() <= TOL[ctype], i
+    z = golden["transpose"]
+    n = int(z["n"])
+    for i in range(int(z["n_cases"])):
+        dt = str(z[f"t{i}_dtype"])
+        a = (np.arange(2 ** n, dtype=np.int64) * 5 + 1).astype(dt).reshape((2,) * n)
+        out = hb.transpose(a, z[f"t{i}_axes"])
+        assert np.array_equal(out.reshape(-1), z[f"t{i}_out"]), i
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_swap_dev_and_permute_bits(hb, oracle, ctype):
+    rng = np.random.default_rng(23)
+    n = 16
+    psi = _rand_state(rng, n, ctype)
+    for trial in range(6):
+        m = int(rng.integers(2, 11))
+        pos = rng.permutation(m)
+        out = hb.DeviceState(n, ctype).upload(psi).swap(pos).download()
+        assert np.array_equal(out, oracle.numpy_swap(psi, pos)), (trial, "swap")      # bit-exact
+        perm = rng.permutation(n)
+        out = hb.DeviceState(n, ctype).upload(psi).permute_bits(perm).download()
+        assert np.array_equal(out, oracle.numpy_swap(psi, perm)), (trial, "perm")
+
+
+def test_init_product_and_reductions(hb):
+    n = 14
+    for ctype in ("complex64", "complex128"):
+        for spec in ("0" * n, "+-01" * 3 + "1+", "1" * n):
+            st = hb.DeviceState(n, ctype).init_product(spec)
+            ref = product_state(spec, ctype)
+            assert np.abs(st.download() - ref).max() < (1e-6 if ctype == "complex64" else 1e-14)
+            assert abs(st.norm2() - 1) < 1e-5
+        a = hb.DeviceState(n, ctype).init_random(seed=5)
+        b = hb.DeviceState(n, ctype).init_random(seed=6)
+        ha, hbb = a.download(), b.download()
+        assert abs(a.norm2() - 1) < 1e-6
+        assert abs(a.vdot(b) - np.vdot(ha.astype(np.complex128), hbb.astype(np.complex128))) < 1e-6
+
+
+def test_functional_gate_round_trip(hb, oracle, c_oracle):
+    """FunctionalGate contract (simulation.py:525-554): gets split planes + order on the host."""
+    from hybridq_b200.circuits import matching_circuit, to_positions
+
+    class Project0:                      # zero the amplitudes where the first qubit is 1
+        qubits = (0,)
+
+        def apply(self, psi, order):
+            assert psi.shape[0] == 2 and order[0] == 0
+            psi = psi.copy()
+            psi[:, 1] = 0
+            return psi, order
+
+    n = 12
+    gates = matching_circuit(n, depth=3, seed=3)
+    mixed = gates[:10] + [Project0()] + gates[10:]
+    out = hb.simulate(mixed, initial_state="+" * n, complex_type="complex128")
+    lowered, _ = to_positions(gates)
+    psi = product_state("+" * n, "complex128")
+    psi = oracle.evolve_oracle(psi, lowered[:10], c_oracle)
+    psi = psi.reshape((2,) * n).copy()
+    psi[1] = 0
+    psi = oracle.evolve_oracle(psi.reshape(-1), lowered[10:], c_oracle)
+    assert np.abs(out.reshape(-1) - psi).max() <= 1e-12
+
+
+# ------------------------------------------------------------------ BASELINE sizes: properties
+@pytest.mark.parametrize("n,ctype", [(30, "complex64"), (29, "complex128")])
+def test_full_size_round_trip_and_norm(hb, n, ctype):
+    """No CPU oracle finishes in seconds at this size: check size-independent properties.
+    U then U^dagger (reversed circuit) must return the initial state; the norm is preserved;
+    a fused plan and a one-gate-per-pass plan must agree."""
+    from hybridq_b200.circuits import matching_circuit, ksweep_circuit, to_positions
+    gates = matching_circuit(n, depth=2, seed=n) + ksweep_circuit(n, 3, 2) + ksweep_circuit(n, 5, 1)
+    lowered, _ = to_positions(gates)
+    inverse = [(U.conj().T, p) for U, p in reversed(lowered)]
+    st = hb.DeviceState(n, ctype).init_random(seed=n)
+    ref = st.copy()
+    fwd = hb.Plan(lowered, n, ctype)
+    bwd = hb.Plan(inverse, n, ctype, hb.PlanOptions(0, -1, 0, 0, 0))      # unfused on the way back
+    fwd.run(st)
+    n2 = st.norm2()
+    assert abs(n2 - 1) < (1e-4 if ctype == "complex64" else 1e-10)
+    ov_mid = abs(ref.vdot(st))
+    assert ov_mid < 0.5                       # the circuit really changed the state
+    bwd.run(st)
+    ov = ref.vdot(st)
+    assert abs(ov - 1) < (1e-4 if ctype == "complex64" else 1e-10)
+    # element-wise: max-abs deviation from the initial state
+    import torch
+    err = float((st.tensor - ref.tensor).abs().max())
+    assert err <= TOL[ctype], err
