@@ -11,7 +11,7 @@ missing: there is no CPU fallback.  Public surface:
                               reference loads this library as ``hybridq.so`` / ``hybridq_swap.so``
 """
 from ._lib import lib, PlanOptions, HybridQB200Error, DROPIN_DIR, LIBPATH  # noqa: F401
-from .state import DeviceState, Plan  # noqa: F401
+from .state import DeviceState, Plan, BitPermPlan  # noqa: F401
 from .simulate import simulate  # noqa: F401
 from .dot import dot, transpose, to_complex  # noqa: F401
 from . import circuits  # noqa: F401

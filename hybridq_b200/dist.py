@@ -1,0 +1,347 @@
+"""State-vector sharding across GPUs: one process per GPU, the top g = log2(p) index bits are
+the rank, every rank holds 2^(n-g) amplitudes.
+
+The reference has no counterpart: its evolution path refuses MPI
+(/root/reference/hybridq/circuit/simulation/simulation.py:379-380) and
+``examples/example-mpi.py:70-73`` replicates the evolution on every rank.  What is mirrored
+is the bookkeeping idea of its host loop -- a logical->physical bit map that is only
+restored at the end (simulation.py:512-513, :615-619, :655-663) -- lifted from "low bits of
+one buffer" to "bits that are the rank".
+
+Schedule (computed identically on every rank, pure Python, no communication):
+
+  local     run every pending gate whose targets are all local bits (skipping over blocked
+            gates when they commute, like the fuser) as fused tile passes;
+  remap     choose the new set of g rank bits = the logical bits whose next use is farthest
+            away (Belady), move the bits that must become rank bits to the top of the local
+            index with one in-place bit-permutation pass, then EXCHANGE: every rank swaps
+            (2^s - 1)/2^s of its shard with the 2^s - 1 ranks that differ in the s rank bits
+            being replaced (grouped NCCL send/recv into the second buffer, ping-pong);
+  restore   at the end of the circuit put every logical bit back in place (<= 2 exchanges
+            + one local permutation), so the result is in canonical order.
+
+The local work is delegated to an *engine*; the product engine is :class:`CudaEngine`
+(hand-written kernels through the C ABI).  The CPU-only tests inject an oracle-backed
+engine to exercise this scheduling and the gloo send/recv pattern without a GPU -- the
+product never does that.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Sequence
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------
+# schedule
+# ------------------------------------------------------------------------------------------
+class Op:
+    __slots__ = ("kind", "gates", "gate_ids", "perm", "gbits", "moved_frac")
+
+    def __init__(self, kind, gates=None, gate_ids=None, perm=None, gbits=None):
+        self.kind = kind            # 'local' | 'permute' | 'exchange'
+        self.gates = gates          # [(U, physical positions)]
+        self.gate_ids = gate_ids
+        self.perm = perm            # local bit permutation: new bit i <- old bit perm[i]
+        self.gbits = gbits          # rank-bit indices (0..g-1) swapped with the top local bits
+
+
+def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
+    """Turn [(U, logical positions)] into a list of Ops for p = 2^g ranks."""
+    nl = n - g
+    where = list(range(n))                      # logical bit -> physical bit (>= nl: rank bit)
+    ops: list[Op] = []
+    pending = list(range(len(lowered)))
+    stats = {"exchanges": 0, "exchange_bits": 0, "permutes": 0, "moved_shard_fraction": 0.0,
+             "crossing_gates": sum(1 for _, p in lowered if any(b >= nl for b in p)),
+             "gates": len(lowered)}
+
+    while pending:
+        blocked: set[int] = set()
+        run, rest = [], []
+        for gi in pending:
+            bits = lowered[gi][1]
+            if any(b in blocked for b in bits) or any(where[b] >= nl for b in bits):
+                blocked.update(bits)
+                rest.append(gi)
+            else:
+                run.append(gi)
+        if run:
+            ops.append(Op("local", gates=[(lowered[gi][0], [where[b] for b in lowered[gi][1]]) for gi in run],
+                          gate_ids=run))
+        pending = rest
+        if not pending:
+            break
+        first_use = {}
+        for idx, gi in enumerate(pending):
+            for b in lowered[gi][1]:
+                first_use.setdefault(b, idx)
+        # farthest next use first; ties: keep current rank bits, then higher logical bits
+        order = sorted(range(n), key=lambda b: (-first_use.get(b, math.inf), where[b] < nl, -b))
+        emit_remap_ordered(ops, stats, where, n, nl, order[:g])
+
+    if restore and g > 0:
+        for _ in range(2):
+            cur_global = [b for b in range(n) if where[b] >= nl]
+            if all(where[b] == b for b in cur_global):
+                break
+            # keep the correctly placed rank bits; vacated positions receive their own logical bit
+            # when it is local now, otherwise any low logical bit (the second round fixes those)
+            new_global = [b for b in cur_global if where[b] == b]
+            need = g - len(new_global)
+            cands = [b for b in range(nl, n) if where[b] < nl][:need]
+            fill = [b for b in range(nl) if where[b] < nl]
+            new_global += cands + fill[:need - len(cands)]
+            emit_remap_ordered(ops, stats, where, n, nl, new_global)
+        if any(where[i] != i for i in range(nl)):
+            # new bit i <- old bit where[i] (logical bit i currently lives at physical where[i])
+            ops.append(Op("permute", perm=[where[i] for i in range(nl)]))
+            stats["permutes"] += 1
+            for i in range(nl):
+                where[i] = i
+    return ops, stats, where
+
+
+def emit_remap_ordered(ops, stats, where, n, nl, new_global):
+    """Exchange so that the rank bits become `new_global`, placing logical bit b at rank position
+    b - nl whenever b >= nl is among the incoming bits and that position is being vacated."""
+    cur_global = [b for b in range(n) if where[b] >= nl]
+    s_out = sorted([b for b in cur_global if b not in new_global], key=lambda b: where[b])
+    s_in = [b for b in new_global if b not in cur_global]
+    s = len(s_out)
+    if s == 0:
+        return
+    # match incoming bits to vacated rank positions
+    slots = [where[b] for b in s_out]                 # physical rank positions being vacated
+    assigned = [None] * s
+    rest = []
+    for b in s_in:
+        if b >= nl and b in slots:
+            assigned[slots.index(b)] = b
+        else:
+            rest.append(b)
+    for j in range(s):
+        if assigned[j] is None:
+            assigned[j] = rest.pop(0)
+    s_in = assigned
+    inv = [0] * n
+    for b in range(n):
+        inv[where[b]] = b
+    perm = list(range(nl))
+    moved = False
+    for j, b in enumerate(s_in):
+        tgt = nl - s + j
+        src = where[b]
+        if src != tgt:
+            other = inv[tgt]
+            perm[tgt], perm[src] = perm[src], perm[tgt]
+            where[b], where[other] = tgt, src
+            inv[tgt], inv[src] = b, other
+            moved = True
+    if moved:
+        ops.append(Op("permute", perm=perm))
+        stats["permutes"] += 1
+    ops.append(Op("exchange", gbits=[p - nl for p in slots]))
+    stats["exchanges"] += 1
+    stats["exchange_bits"] += s
+    stats["moved_shard_fraction"] += (2 ** s - 1) / 2 ** s
+    for j, (bo, bi) in enumerate(zip(s_out, s_in)):
+        where[bo], where[bi] = nl - s + j, slots[j]
+
+
+# ------------------------------------------------------------------------------------------
+# exchange
+# ------------------------------------------------------------------------------------------
+def exchange(dist, src, dst, rank: int, gbits: Sequence[int]):
+    """Swap rank bits `gbits` (ascending) with the top s = len(gbits) local index bits.
+    `src`, `dst`: 1-D tensors holding the shard; the result is written to `dst`.
+    Chunk D of the shard (value of the top s local bits) goes to the rank whose bits `gbits`
+    equal D and is replaced by that rank's chunk number my_bits."""
+    s = len(gbits)
+    chunks = 1 << s
+    size = src.numel() // chunks
+    mine = 0
+    for j, gb in enumerate(gbits):
+        mine |= ((rank >> gb) & 1) << j
+    ops = []
+    for D in range(chunks):
+        if D == mine:
+            continue
+        partner = rank
+        for j, gb in enumerate(gbits):
+            partner = (partner & ~(1 << gb)) | (((D >> j) & 1) << gb)
+        ops.append(dist.P2POp(dist.isend, src[D * size:(D + 1) * size], partner))
+        ops.append(dist.P2POp(dist.irecv, dst[D * size:(D + 1) * size], partner))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    dst[mine * size:(mine + 1) * size].copy_(src[mine * size:(mine + 1) * size])
+    for r in reqs:
+        r.wait()
+
+
+# ------------------------------------------------------------------------------------------
+# engines
+# ------------------------------------------------------------------------------------------
+class CudaEngine:
+    """Local work on the GPU through libhybridq_b200.so."""
+
+    def __init__(self, n_local: int, ctype, plan_options=None):
+        import hybridq_b200 as hb
+        self.hb = hb
+        self.n_local = n_local
+        self.ctype = np.dtype(ctype)
+        self.plan_options = plan_options
+        self._plans = {}
+
+    def alloc(self):
+        return self.hb.DeviceState(self.n_local, self.ctype)
+
+    def tensor(self, st):
+        return st.tensor
+
+    def run_gates(self, st, key, gates):
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self.hb.Plan(gates, self.n_local, self.ctype, self.plan_options)
+        plan.run(st)
+        return plan.n_passes
+
+    def permute(self, st, key, perm):
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self.hb.BitPermPlan(perm, self.n_local, self.ctype)
+        plan.run(st)
+        return plan.n_passes
+
+    def init_random(self, st, seed, index_offset):
+        st.init_random(seed=seed, index_offset=index_offset, scale=1.0)
+
+    def norm2(self, st):
+        return st.norm2()
+
+    def scale(self, st, f):
+        st.scale(f)
+
+    def sync(self):
+        import torch
+        torch.cuda.synchronize()
+
+
+class ShardedRunner:
+    """Executes a sharded schedule; one instance per rank."""
+
+    def __init__(self, n: int, lowered: Sequence, ctype, dist, engine=None, plan_options=None, restore=True):
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.g = int(round(math.log2(self.world)))
+        if 2 ** self.g != self.world:
+            raise ValueError("the number of ranks must be a power of two")
+        self.n = n
+        self.n_local = n - self.g
+        self.ctype = np.dtype(ctype)
+        self.ops, self.stats, self.final_where = plan_sharded(lowered, n, self.g, restore=restore)
+        self.n_gates = len(lowered)
+        self.engine = engine if engine is not None else CudaEngine(self.n_local, ctype, plan_options)
+        self.a = self.engine.alloc()
+        self.b = self.engine.alloc()
+        self.local_passes = 0
+        self.exchange_ms = 0.0
+        self._count_passes = True
+
+    def describe(self):
+        s = self.stats
+        return (f"{self.world} GPUs, top {self.g} index bits = rank; {s['crossing_gates']}/{s['gates']} gates touch a "
+                f"sharded qubit; {s['exchanges']} exchanges ({s['exchange_bits']} bit swaps, "
+                f"{s['moved_shard_fraction']:.2f} shards moved per GPU), {s['permutes']} local permutation passes, "
+                f"{self.local_passes} local tile passes per step")
+
+    def init_state(self, seed: int):
+        self.engine.init_random(self.a, seed, self.rank * (2 ** self.n_local))
+        n2 = self.engine.norm2(self.a)
+        tot = self._allreduce_sum(n2)
+        self.engine.scale(self.a, 1.0 / math.sqrt(tot))
+
+    def _allreduce_sum(self, v: float) -> float:
+        import torch
+        t = self.engine.tensor(self.a)
+        x = torch.tensor([v], dtype=torch.float64, device=t.device)
+        self.dist.all_reduce(x)
+        return float(x.item())
+
+    def norm2(self) -> float:
+        return self._allreduce_sum(self.engine.norm2(self.a))
+
+    def step(self, time_exchange: bool = False):
+        passes = 0
+        for i, op in enumerate(self.ops):
+            if op.kind == "local":
+                passes += self.engine.run_gates(self.a, ("g", i), op.gates)
+            elif op.kind == "permute":
+                passes += self.engine.permute(self.a, ("p", i), op.perm)
+            else:
+                if time_exchange:
+                    self.engine.sync()
+                    t0 = time.perf_counter()
+                exchange(self.dist, self.engine.tensor(self.a), self.engine.tensor(self.b), self.rank, op.gbits)
+                self.a, self.b = self.b, self.a
+                if time_exchange:
+                    self.engine.sync()
+                    self.exchange_ms += 1e3 * (time.perf_counter() - t0)
+        self.local_passes = passes
+
+    def kernel_time_ms(self, reps: int = 2) -> float:
+        """Device time of the local launches only (no exchanges), CUDA events."""
+        import torch
+        total = 0.0
+        for _ in range(reps):
+            for i, op in enumerate(self.ops):
+                if op.kind == "exchange":
+                    continue
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if op.kind == "local":
+                    self.engine.run_gates(self.a, ("g", i), op.gates)
+                else:
+                    self.engine.permute(self.a, ("p", i), op.perm)
+                e1.record()
+                torch.cuda.synchronize()
+                total += e0.elapsed_time(e1)
+        return total / reps
+
+    def gather(self):
+        """Full state on every rank (tests / small n only), canonical order required."""
+        import torch
+        t = self.engine.tensor(self.a)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return torch.cat(out).cpu().numpy()
+
+    def e2e(self, gates, steps, barrier, dist):
+        """Pinned host shard in -> circuit -> pinned host shard out, per rank."""
+        import torch
+        t = self.engine.tensor(self.a)
+        host_in = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        host_out = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        host_in.zero_()
+        if self.rank == 0:
+            host_in[0] = 1
+        for it in range(steps + 1):
+            if it == 1:
+                barrier()
+                t0 = time.perf_counter()
+            self.engine.tensor(self.a).copy_(host_in, non_blocking=True)
+            self.step()
+            host_out.copy_(self.engine.tensor(self.a), non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        x = torch.tensor([dt], dtype=torch.float64, device=t.device)
+        dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        dt = float(x.item())
+        nbytes = t.numel() * t.element_size()
+        return {"value": self.n_gates * steps / dt, "unit": "gate-applies/s",
+                "h2d_bytes_per_step": nbytes * self.world, "d2h_bytes_per_step": nbytes * self.world,
+                "ms_per_step": 1e3 * dt / steps, "steps": steps,
+                "api": "hybridq_b200.dist.ShardedRunner: pinned host shard -> HBM, step(), HBM -> pinned host shard"}

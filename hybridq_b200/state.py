@@ -86,6 +86,36 @@ class Plan:
                                         _stream_handle(stream)), "hq_plan_run_range")
 
 
+class BitPermPlan:
+    """In-place permutation of index bits as tile passes (hq_plan_create_bitperm):
+    new index bit i <- old index bit perm[i]."""
+
+    def __init__(self, perm: Sequence[int], n_qubits: int, complex_type="complex64",
+                 options: PlanOptions | None = None):
+        self.n_qubits = int(n_qubits)
+        self.dtype = _lib.dtype_code(complex_type)
+        perm = np.ascontiguousarray(perm, dtype=np.uint32)
+        if len(perm) != self.n_qubits:
+            raise ValueError("perm must list every bit")
+        self._h = lib.hq_plan_create_bitperm(self.dtype, self.n_qubits,
+                                             perm.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                             ctypes.byref(options or PlanOptions()))
+        if not self._h:
+            raise _lib.HybridQB200Error(f"hq_plan_create_bitperm failed: {_lib.last_error()}")
+        self.n_passes = lib.hq_plan_num_passes(self._h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.hq_plan_destroy(h)
+            self._h = None
+
+    def run(self, state: "DeviceState", stream=None):
+        if state.n_qubits != self.n_qubits or state.dtype != self.dtype:
+            raise ValueError("plan and state disagree on size or precision")
+        check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream)), "hq_plan_run")
+
+
 class DeviceState:
     def __init__(self, n_qubits: int, complex_type="complex64", device: int | None = None, tensor=None):
         import torch
@@ -190,17 +220,6 @@ class DeviceState:
 
     def permute_bits(self, perm: Sequence[int], options: PlanOptions | None = None, stream=None):
         """new index bit i <- old index bit perm[i] for every i < n (in place)."""
-        perm = np.ascontiguousarray(perm, dtype=np.uint32)
-        if len(perm) != self.n_qubits:
-            raise ValueError("perm must list every bit")
-        h = lib.hq_plan_create_bitperm(self.dtype, self.n_qubits,
-                                       perm.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
-                                       ctypes.byref(options or PlanOptions()))
-        if not h:
-            raise _lib.HybridQB200Error(f"hq_plan_create_bitperm failed: {_lib.last_error()}")
-        try:
-            check(lib.hq_plan_run(h, self.ptr, _stream_handle(stream)), "hq_plan_run")
-            check(lib.hq_stream_sync(_stream_handle(stream)), "sync")
-        finally:
-            lib.hq_plan_destroy(h)
+        BitPermPlan(perm, self.n_qubits, self.complex_type, options).run(self, stream)
+        self.sync(stream)
         return self
