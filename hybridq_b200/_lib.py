@@ -40,10 +40,13 @@ _vp = ctypes.c_void_p
 
 class PlanOptions(ctypes.Structure):
     _fields_ = [("tile_bits", ctypes.c_int), ("min_run_bits", ctypes.c_int), ("fuse", ctypes.c_int),
-                ("max_gates_per_pass", ctypes.c_int), ("lookahead", ctypes.c_int)]
+                ("max_gates_per_pass", ctypes.c_int), ("lookahead", ctypes.c_int),
+                ("merge_max_k", ctypes.c_int), ("merge_pass_cost", ctypes.c_int)]
 
-    def __init__(self, tile_bits=0, min_run_bits=-1, fuse=1, max_gates_per_pass=0, lookahead=0):
-        super().__init__(tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead)
+    def __init__(self, tile_bits=0, min_run_bits=-1, fuse=1, max_gates_per_pass=0, lookahead=0,
+                 merge_max_k=-1, merge_pass_cost=-1):
+        super().__init__(tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead, merge_max_k,
+                         merge_pass_cost)
 
 
 def _proto(name, restype, *argtypes):
@@ -95,6 +98,7 @@ _proto("hq_plan_create_bitperm", _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes
 _proto("hq_plan_destroy", None, _vp)
 _proto("hq_plan_num_passes", ctypes.c_int, _vp)
 _proto("hq_plan_num_gates", ctypes.c_int, _vp)
+_proto("hq_plan_num_kernel_gates", ctypes.c_int, _vp)
 _proto("hq_plan_pass_info", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int)
 _proto("hq_plan_pass_gates", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int)
 _proto("hq_plan_run", ctypes.c_int, _vp, _vp, _vp)
@@ -111,7 +115,7 @@ EXPORTED = [
     "hq_stream_sync", "hq_apply_U_dev", "hq_apply_U_direct_dev", "hq_swap_dev", "hq_pack_dev",
     "hq_unpack_dev", "hq_init_product_dev", "hq_init_random_dev", "hq_norm2_dev", "hq_vdot_dev",
     "hq_scale_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
-    "hq_plan_num_gates", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
+    "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
     "hq_set_tuning", "hq_launch_count", "hq_launch_count_reset",
 ]
 

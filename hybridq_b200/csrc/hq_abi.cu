@@ -199,6 +199,8 @@ hq::PlanOptions convert_opts(const hq_plan_options* o) {
     p.fuse = o->fuse;
     p.max_gates_per_pass = o->max_gates_per_pass;
     p.lookahead = o->lookahead;
+    p.merge_max_k = o->merge_max_k;
+    p.merge_pass_cost = o->merge_pass_cost;
   }
   return p;
 }
@@ -451,16 +453,18 @@ void hq_plan_destroy(hq_plan* plan) {
 }
 int hq_plan_num_passes(const hq_plan* plan) { return plan ? int(plan->plan.passes.size()) : -1; }
 int hq_plan_num_gates(const hq_plan* plan) { return plan ? int(plan->plan.n_gates) : -1; }
+int hq_plan_num_kernel_gates(const hq_plan* plan) { return plan ? int(plan->plan.n_kernel_gates) : -1; }
 
 int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len) {
   if (!plan || pass < 0 || pass >= int(plan->plan.passes.size())) return fail("bad pass index", 1);
   const HqPassHeader& ph = plan->plan.passes[size_t(pass)].header;
-  if (out_len < 4 + int(ph.n_high)) return fail("output too small", 1);
+  if (out_len < 5 + int(ph.n_high)) return fail("output too small", 1);
   out[0] = ph.tile_bits;
   out[1] = ph.n_high;
   out[2] = ph.n_gates;
   out[3] = ph.has_perm;
-  for (unsigned i = 0; i < ph.n_high; ++i) out[4 + i] = ph.high_pos[i];
+  out[4] = unsigned(plan->plan.passes[size_t(pass)].gate_ids.size());
+  for (unsigned i = 0; i < ph.n_high; ++i) out[5 + i] = ph.high_pos[i];
   return 0;
 }
 int hq_plan_pass_gates(const hq_plan* plan, int pass, unsigned int* out, int out_len) {

@@ -81,6 +81,8 @@ hq::PlanOptions make_opts(const int* o) {
     p.fuse = o[2];
     p.max_gates_per_pass = o[3];
     p.lookahead = o[4];
+    p.merge_max_k = o[5];
+    p.merge_pass_cost = o[6];
   }
   return p;
 }
@@ -89,7 +91,7 @@ hq::PlanOptions make_opts(const int* o) {
 
 extern "C" {
 
-// opts = {tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead} or NULL.
+// opts = {tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead, merge_max_k, merge_pass_cost} or NULL.
 // info_out (optional, >= 2 ints) receives {n_passes, n_gates}.
 int hq_emu_run_circuit(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
                        const double* U_flat, const int* opts, void* state_interleaved, int* info_out,
@@ -115,6 +117,7 @@ int hq_emu_run_circuit(int dtype, unsigned n, unsigned n_gates, const unsigned* 
   if (info_out) {
     info_out[0] = int(plan.passes.size());
     info_out[1] = int(plan.n_gates);
+    info_out[2] = int(plan.n_kernel_gates);
   }
   return 0;
 }
@@ -133,7 +136,7 @@ int hq_emu_bitperm(int dtype, unsigned n, const unsigned* perm, const int* opts,
 }
 
 // planner introspection for host-logic tests: passes as flat records
-// {tile_bits, n_high, n_gates, has_perm, high_pos..., gate ids...}; returns words written or -1.
+// {tile_bits, n_high, n_kernel_gates, has_perm, n_ids, high_pos..., gate ids...}; returns words written or -1.
 int hq_emu_plan_dump(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
                      const int* opts, unsigned* out, int out_len) {
   std::vector<hq::GateIn> gates(n_gates);
@@ -149,12 +152,13 @@ int hq_emu_plan_dump(int dtype, unsigned n, unsigned n_gates, const unsigned* ks
   if (hq::plan_build(plan, dtype, n, gates, make_opts(opts))) return -1;
   int w = 0;
   for (const hq::PassInfo& pi : plan.passes) {
-    const int need = 4 + int(pi.header.n_high) + int(pi.gate_ids.size());
+    const int need = 5 + int(pi.header.n_high) + int(pi.gate_ids.size());
     if (w + need > out_len) return -1;
     out[w++] = pi.header.tile_bits;
     out[w++] = pi.header.n_high;
     out[w++] = pi.header.n_gates;
     out[w++] = pi.header.has_perm;
+    out[w++] = unsigned(pi.gate_ids.size());
     for (unsigned i = 0; i < pi.header.n_high; ++i) out[w++] = pi.header.high_pos[i];
     for (unsigned id : pi.gate_ids) out[w++] = id;
   }

@@ -47,8 +47,8 @@ __device__ __forceinline__ void st_stream(Unit* p, const Unit& v) {
 // blockIdx.x + gridDim.x, ...  With NBUF = 2 the fill of the CTA's next tile is issued
 // (cp.async, no registers involved) before the gates of the current tile run, so every CTA
 // keeps one whole tile of loads in flight while it computes and drains.
-// KCLASS: 0 = passes whose gates all have k <= 2, 1 = k <= 4, 2 = anything (adds the
-// two-phase path); the narrower classes need far fewer registers.
+// KCLASS: 0 = passes whose gates all have k <= 2, 1 = k <= 3, 2 = k <= 4, 3 = anything (adds
+// the two-phase path); the narrower classes need far fewer registers.
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void tile_fill(typename Traits<T>::Unit* tile,
@@ -61,13 +61,13 @@ __device__ __forceinline__ void tile_fill(typename Traits<T>::Unit* tile,
 }
 
 template <typename T, int KCLASS, int NBUF>
-__global__ void __launch_bounds__(HQ_THREADS, (KCLASS == 0 ? 3 : 2))
+__global__ void __launch_bounds__(HQ_THREADS, (KCLASS <= 1 ? 3 : 2))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
                const HqPassHeader ph, const unsigned long long n_tiles) {
   typedef typename Traits<T>::Unit Unit;
   typedef typename Traits<T>::Cplx Cplx;
   const int V = Traits<T>::V;
-  const int MAXK = KCLASS == 0 ? 2 : 4;
+  const int MAXK = KCLASS == 0 ? 2 : (KCLASS == 1 ? 3 : 4);
   extern __shared__ __align__(16) unsigned char smem[];
 
   const int tid = threadIdx.x;
@@ -125,7 +125,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
 
     for (uint32_t gi = 0; gi < n_gates; ++gi) {
       const HqGateDesc& g = gd[gi];
-      if (KCLASS < 2 || g.kind == HQ_GATE_SMALL) {
+      if (KCLASS < 3 || g.kind == HQ_GATE_SMALL) {
         gate_small_dispatch<MAXK>(tile, g, prog, Tu, tid);
       } else {
         const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + g.mat_off);
@@ -230,13 +230,14 @@ static int launch_tile_pass_t(void* state, unsigned n_qubits, const unsigned cha
   if (ph.tile_bits > n_qubits) return int(cudaErrorInvalidValue);
   const size_t smem = tile_pass_smem_bytes(ph, dtype);
   if (smem > size_t(di.max_smem_optin)) return int(cudaErrorInvalidValue);
-  const int kclass = ph.max_k <= 2 ? 0 : (ph.max_k <= 4 ? 1 : 2);
+  const int kclass = ph.max_k <= 2 ? 0 : (ph.max_k <= 3 ? 1 : (ph.max_k <= 4 ? 2 : 3));
   const bool two = g_tune_nbuf == 2;
 #define HQ_LAUNCH(KC, NB) launch_tile_variant<T, KC, NB>(state, n_qubits, prog, ph, stream, grid_override, smem, di, dev)
   switch (kclass) {
     case 0: return two ? HQ_LAUNCH(0, 2) : HQ_LAUNCH(0, 1);
     case 1: return two ? HQ_LAUNCH(1, 2) : HQ_LAUNCH(1, 1);
-    default: return two ? HQ_LAUNCH(2, 2) : HQ_LAUNCH(2, 1);
+    case 2: return two ? HQ_LAUNCH(2, 2) : HQ_LAUNCH(2, 1);
+    default: return two ? HQ_LAUNCH(3, 2) : HQ_LAUNCH(3, 1);
   }
 #undef HQ_LAUNCH
 }

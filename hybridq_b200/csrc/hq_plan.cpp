@@ -119,6 +119,97 @@ void write_matrix(std::vector<unsigned char>& prog, size_t off, const Canon& c, 
     }
 }
 
+// ---- in-pass merging -------------------------------------------------------------------
+// Embed `c` (ascending positions) into the ascending superset `pos_u`.
+std::vector<std::complex<double>> embed(const Canon& c, const std::vector<unsigned>& pos_u) {
+  const unsigned ku = unsigned(pos_u.size());
+  const size_t dim = size_t(1) << ku;
+  std::vector<unsigned> slot(c.k);          // matrix bit i of c -> matrix bit slot[i] of the union
+  for (unsigned i = 0; i < c.k; ++i)
+    slot[i] = unsigned(std::find(pos_u.begin(), pos_u.end(), c.pos[i]) - pos_u.begin());
+  size_t cmask = 0;
+  for (unsigned i = 0; i < c.k; ++i) cmask |= size_t(1) << slot[i];
+  auto sub = [&](size_t a) {
+    size_t r = 0;
+    for (unsigned i = 0; i < c.k; ++i) r |= ((a >> slot[i]) & 1u) << i;
+    return r;
+  };
+  const size_t cd = size_t(1) << c.k;
+  std::vector<std::complex<double>> out(dim * dim, std::complex<double>(0, 0));
+  for (size_t a = 0; a < dim; ++a)
+    for (size_t b = 0; b < dim; ++b)
+      if ((a & ~cmask) == (b & ~cmask)) out[a * dim + b] = c.U[sub(a) * cd + sub(b)];
+  return out;
+}
+
+// first := second * first on the union of their positions (second is applied after first).
+void merge_into(Canon& first, const Canon& second) {
+  std::vector<unsigned> pos_u = first.pos;
+  for (unsigned p : second.pos)
+    if (std::find(pos_u.begin(), pos_u.end(), p) == pos_u.end()) pos_u.push_back(p);
+  std::sort(pos_u.begin(), pos_u.end());
+  const size_t dim = size_t(1) << pos_u.size();
+  const std::vector<std::complex<double>> A = embed(second, pos_u), B = embed(first, pos_u);
+  std::vector<std::complex<double>> C(dim * dim, std::complex<double>(0, 0));
+  for (size_t i = 0; i < dim; ++i)
+    for (size_t l = 0; l < dim; ++l) {
+      const std::complex<double> a = A[i * dim + l];
+      if (a == std::complex<double>(0, 0)) continue;
+      for (size_t j = 0; j < dim; ++j) C[i * dim + j] += a * B[l * dim + j];
+    }
+  first.k = unsigned(pos_u.size());
+  first.pos = pos_u;
+  first.U.swap(C);
+}
+
+struct Cluster {
+  Canon gate;
+  std::vector<unsigned> ids;       // canonical-gate indices merged in, in application order
+  uint64_t mask = 0;
+};
+
+int union_k(uint64_t a, uint64_t b) { return __builtin_popcountll(a | b); }
+
+// Greedy merging of an ordered gate list (all inside one tile).
+std::vector<Cluster> merge_pass(const std::vector<Canon>& canon, const std::vector<unsigned>& ids, int max_k,
+                                int pass_cost) {
+  std::vector<Cluster> cl;
+  auto cost = [&](int k) { return 4 * (1 << k) + pass_cost; };
+  for (unsigned id : ids) {
+    const Canon& g = canon[id];
+    uint64_t gm = 0;
+    for (unsigned p : g.pos) gm |= uint64_t(1) << p;
+    int target = -1;
+    if (max_k > 0 && int(g.k) <= max_k) {
+      int best_gain = -1;
+      for (int c = int(cl.size()) - 1; c >= 0; --c) {
+        const int ku = union_k(cl[size_t(c)].mask, gm);
+        if (ku <= max_k && ku <= HQ_SMALL_K) {
+          const int gain = cost(int(cl[size_t(c)].gate.k)) + cost(int(g.k)) - cost(ku);
+          // prefer the cluster that shares bits with g (later ones are disjoint by construction)
+          if (gain >= 0 && gain > best_gain) {
+            best_gain = gain;
+            target = c;
+          }
+        }
+        if (cl[size_t(c)].mask & gm) break;       // g cannot move before a gate it overlaps
+      }
+    }
+    if (target >= 0) {
+      merge_into(cl[size_t(target)].gate, g);
+      cl[size_t(target)].ids.push_back(id);
+      cl[size_t(target)].mask |= gm;
+    } else {
+      Cluster c;
+      c.gate = g;
+      c.ids.push_back(id);
+      c.mask = gm;
+      cl.push_back(std::move(c));
+    }
+  }
+  return cl;
+}
+
 }  // namespace
 
 int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gates_in,
@@ -200,31 +291,39 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     drafts.push_back(std::move(d));
   }
 
-  // ---- serialise
+  // ---- merge inside each pass, then serialise
+  const int merge_max_k = opts.merge_max_k < 0 ? 4 : std::min(opts.merge_max_k, HQ_SMALL_K);
+  const int merge_pass_cost = opts.merge_pass_cost < 0 ? 12 : opts.merge_pass_cost;
+  std::vector<std::vector<Cluster>> merged(drafts.size());
   size_t total_gates = 0;
-  for (const Draft& d : drafts) total_gates += d.ids.size();
+  size_t mat_bytes = 0;
+  const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
+  for (size_t d = 0; d < drafts.size(); ++d) {
+    merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost);
+    total_gates += merged[d].size();
+    for (const Cluster& c : merged[d]) mat_bytes += ((esz << (2 * c.gate.k)) + 15) & ~size_t(15);
+  }
+  plan.n_kernel_gates = unsigned(total_gates);
   size_t off = total_gates * sizeof(HqGateDesc);
   off = (off + 15) & ~size_t(15);
   const size_t mat_base = off;
-  size_t mat_bytes = 0;
-  const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
-  for (const Canon& c : canon) mat_bytes += ((esz << (2 * c.k)) + 15) & ~size_t(15);
   plan.program.assign(mat_base + mat_bytes + 16, 0);
 
   size_t gate_cursor = 0;
   size_t mat_cursor = mat_base;
-  for (const Draft& d : drafts) {
+  for (size_t di = 0; di < drafts.size(); ++di) {
+    const Draft& d = drafts[di];
     PassInfo pi;
     // single gates may use shorter runs than the fuser is allowed to create
     int L = choose_run_bits(d.bits, T, d.ids.size() > 1 ? fuse_min_run : hard_min_run);
     if (L < 0) { plan.error = "internal: pass does not fit"; return 1; }
     make_tile(d.bits, T, L, n, pi.header);
-    pi.header.n_gates = uint32_t(d.ids.size());
+    pi.header.n_gates = uint32_t(merged[di].size());
     pi.header.gates_off = uint32_t(gate_cursor * sizeof(HqGateDesc));
     const int Tbits = int(pi.header.tile_bits);
     const int Tu = Tbits - V;
-    for (unsigned id : d.ids) {
-      const Canon& c = canon[id];
+    for (const Cluster& cluster : merged[di]) {
+      const Canon& c = cluster.gate;
       HqGateDesc gd;
       memset(&gd, 0, sizeof(gd));
       gd.k = c.k;
@@ -257,7 +356,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         write_matrix<double>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
       mat_cursor += ((esz << (2 * c.k)) + 15) & ~size_t(15);
       ++gate_cursor;
-      pi.gate_ids.push_back(canon_id[id]);
+      for (unsigned id : cluster.ids) pi.gate_ids.push_back(canon_id[id]);
       pi.header.max_k = std::max<uint32_t>(pi.header.max_k, c.k);
     }
     plan.passes.push_back(std::move(pi));

@@ -29,6 +29,12 @@ struct PlanOptions {
   int fuse = 1;             // 0: one gate per pass
   int max_gates_per_pass = 0;   // 0 = default (48)
   int lookahead = 0;        // how many gates past the first blocked one the fuser scans; 0 = default
+  // In-pass gate merging (the reference does this on the host too: utils.compress +
+  // to_matrix_gate, /root/reference/hybridq/circuit/utils.py:467, :419, default max 4 qubits).
+  // Two gates of a pass are multiplied into one matrix when that does not raise the cost
+  // cost(k) = 4 * 2^k + merge_pass_cost  (FMA per amplitude + one shared-memory round trip).
+  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (4)
+  int merge_pass_cost = -1; // -1 = default (12)
 };
 
 struct PassInfo {
@@ -40,6 +46,7 @@ struct Plan {
   int dtype = HQ_DTYPE_C64;
   unsigned n_qubits = 0;
   unsigned n_gates = 0;                      // gate-applies covered (k = 0 gates are dropped)
+  unsigned n_kernel_gates = 0;               // matrices the kernels apply after in-pass merging
   std::vector<PassInfo> passes;
   std::vector<unsigned char> program;        // host copy of the device program buffer
   std::string error;

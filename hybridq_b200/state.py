@@ -58,6 +58,7 @@ class Plan:
         if not self._h:
             raise _lib.HybridQB200Error(f"hq_plan_create failed: {_lib.last_error()}")
         self.n_gates = lib.hq_plan_num_gates(self._h)
+        self.n_kernel_gates = lib.hq_plan_num_kernel_gates(self._h)
         self.n_passes = lib.hq_plan_num_passes(self._h)
 
     def __del__(self):
@@ -69,11 +70,12 @@ class Plan:
     def pass_info(self, p: int) -> dict:
         out = (ctypes.c_uint32 * 32)()
         check(lib.hq_plan_pass_info(self._h, p, out, 32), "hq_plan_pass_info")
-        ng = out[2]
+        ng = out[4]
         ids = (ctypes.c_uint32 * max(1, ng))()
         check(lib.hq_plan_pass_gates(self._h, p, ids, max(1, ng)), "hq_plan_pass_gates")
-        return {"tile_bits": out[0], "n_high": out[1], "n_gates": ng, "has_perm": out[3],
-                "high_pos": [out[4 + i] for i in range(out[1])], "gate_ids": [ids[i] for i in range(ng)]}
+        return {"tile_bits": out[0], "n_high": out[1], "n_gates": ng, "n_kernel_gates": out[2],
+                "has_perm": out[3], "high_pos": [out[5 + i] for i in range(out[1])],
+                "gate_ids": [ids[i] for i in range(ng)]}
 
     def run(self, state: "DeviceState", first: int | None = None, last: int | None = None, stream=None):
         if state.n_qubits != self.n_qubits or state.dtype != self.dtype:

@@ -124,6 +124,10 @@ typedef struct hq_plan_options {
   int fuse;                 /* 0 = one pass per gate */
   int max_gates_per_pass;   /* 0 = default */
   int lookahead;            /* 0 = default */
+  int merge_max_k;          /* in-pass merging of gates into one matrix of at most this many qubits
+                               (the reference's host-side `compress`, circuit/utils.py:467);
+                               0 = off, -1 = default (4) */
+  int merge_pass_cost;      /* cost model: cost(k) = 4*2^k + merge_pass_cost; -1 = default (12) */
 } hq_plan_options;
 
 /* gates: n_gates entries; ks[g] = number of target bits; pos_flat = concatenated positions;
@@ -137,7 +141,10 @@ hq_plan* hq_plan_create_bitperm(int dtype, unsigned int n_qubits, const unsigned
 void hq_plan_destroy(hq_plan* plan);
 int hq_plan_num_passes(const hq_plan* plan);
 int hq_plan_num_gates(const hq_plan* plan);
-/* per pass: tile_bits, n_high, n_gates, has_perm, high_pos[0..n_high) -> out[0..4+n_high) */
+/* number of matrices the kernels apply after in-pass merging (<= hq_plan_num_gates) */
+int hq_plan_num_kernel_gates(const hq_plan* plan);
+/* per pass: {tile_bits, n_high, n_kernel_gates, has_perm, n_gate_ids, high_pos[0..n_high)}
+ * -> out[0..5+n_high) */
 int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len);
 /* gate ids (indices into the creation arrays) of a pass, in execution order */
 int hq_plan_pass_gates(const hq_plan* plan, int pass, unsigned int* out, int out_len);

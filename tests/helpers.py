@@ -65,8 +65,8 @@ class Emu:
         n = int(round(np.log2(psi.size)))
         ks, pos, U = self._pack(gates)
         st = np.ascontiguousarray(psi).copy()
-        o = (ctypes.c_int * 5)(*opts) if opts else None
-        info = (ctypes.c_int * 2)()
+        o = (ctypes.c_int * 7)(*(tuple(opts) + (-1, -1))[:7]) if opts else None
+        info = (ctypes.c_int * 3)()
         err = ctypes.create_string_buffer(256)
         rc = self.lib.hq_emu_run_circuit(dt, n, len(gates), ks.ctypes.data_as(ctypes.c_void_p),
                                          pos.ctypes.data_as(ctypes.c_void_p), U.ctypes.data_as(ctypes.c_void_p),
@@ -80,8 +80,8 @@ class Emu:
         n = int(round(np.log2(psi.size)))
         st = np.ascontiguousarray(psi).copy()
         p = np.ascontiguousarray(perm, dtype=np.uint32)
-        o = (ctypes.c_int * 5)(*opts) if opts else None
-        info = (ctypes.c_int * 2)()
+        o = (ctypes.c_int * 7)(*(tuple(opts) + (-1, -1))[:7]) if opts else None
+        info = (ctypes.c_int * 3)()
         err = ctypes.create_string_buffer(256)
         rc = self.lib.hq_emu_bitperm(dt, n, p.ctypes.data_as(ctypes.c_void_p), o,
                                      st.ctypes.data_as(ctypes.c_void_p), info, err, 256)
@@ -93,7 +93,7 @@ class Emu:
         """Planner only: returns list of passes {tile_bits, n_high, n_gates, has_perm, high_pos, gate_ids}."""
         ks = np.array([len(p) for p in gates_pos], dtype=np.uint32)
         pos = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint32) for p in gates_pos]))
-        o = (ctypes.c_int * 5)(*opts) if opts else None
+        o = (ctypes.c_int * 7)(*(tuple(opts) + (-1, -1))[:7]) if opts else None
         out = np.zeros(64 * (len(gates_pos) + 4), dtype=np.uint32)
         w = self.lib.hq_emu_plan_dump(dtype, n, len(gates_pos), ks.ctypes.data_as(ctypes.c_void_p),
                                       pos.ctypes.data_as(ctypes.c_void_p), o,
@@ -102,11 +102,12 @@ class Emu:
             raise RuntimeError("plan failed")
         passes, i = [], 0
         while i < w:
-            T, h, ng, hp = (int(x) for x in out[i:i + 4])
-            i += 4
+            T, h, nk, hp, ng = (int(x) for x in out[i:i + 5])
+            i += 5
             high = [int(x) for x in out[i:i + h]]
             i += h
             ids = [int(x) for x in out[i:i + ng]]
             i += ng
-            passes.append(dict(tile_bits=T, n_high=h, n_gates=ng, has_perm=hp, high_pos=high, gate_ids=ids))
+            passes.append(dict(tile_bits=T, n_high=h, n_gates=ng, n_kernel_gates=nk, has_perm=hp,
+                               high_pos=high, gate_ids=ids))
         return passes

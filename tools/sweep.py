@@ -80,7 +80,7 @@ def main():
                 tiles = [11, 12, 13] if ctype == "complex64" else [10, 11, 12]
                 for T in tiles:
                     for nbuf in (1, 2):
-                        for cps in ((0,) if args.quick else (0, 1, 2)):
+                        for cps in (0,):
                             hb.lib.hq_set_tuning(nbuf, cps)
                             try:
                                 plan = hb.Plan([(U, pos)], n, ctype, hb.PlanOptions(T, -1, 0, 0, 0))
@@ -100,25 +100,25 @@ def main():
         lowered, _ = to_positions(gates, qubits=list(range(n)))
         tiles = [12, 13] if ctype == "complex64" else [11, 12]
         for T in tiles:
-            for min_run in (3, 4, 5, 6):
-                for nbuf in (1, 2):
-                    hb.lib.hq_set_tuning(nbuf, 0)
-                    try:
-                        t0 = time.perf_counter()
-                        plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(T, min_run, 1, 0, 0))
-                        t_plan = time.perf_counter() - t0
-                        ms = timed(lambda: plan.run(st), warm=1, reps=2)
-                    except Exception as e:
+            for min_run in (4, 5):
+                for merge in (0, 2, 3, 4):
+                    for nbuf in (1, 2):
+                        hb.lib.hq_set_tuning(nbuf, 0)
+                        try:
+                            plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(T, min_run, 1, 0, 0, merge, -1))
+                            ms = timed(lambda: plan.run(st), warm=1, reps=2)
+                        except Exception as e:
+                            emit({"what": "circuit", "ctype": ctype, "n": n, "T": T, "min_run": min_run, "nbuf": nbuf,
+                                  "merge": merge, "error": str(e)})
+                            continue
                         emit({"what": "circuit", "ctype": ctype, "n": n, "T": T, "min_run": min_run, "nbuf": nbuf,
-                              "error": str(e)})
-                        continue
-                    emit({"what": "circuit", "ctype": ctype, "n": n, "T": T, "min_run": min_run, "nbuf": nbuf,
-                          "gates": plan.n_gates, "passes": plan.n_passes, "plan_s": t_plan, "ms": ms,
-                          "gate_applies_per_s": plan.n_gates / ms * 1e3,
-                          "GBps_per_pass": bytes_pass * plan.n_passes / ms / 1e6})
+                              "merge": merge, "gates": plan.n_gates, "kernel_gates": plan.n_kernel_gates,
+                              "passes": plan.n_passes, "ms": ms, "gate_applies_per_s": plan.n_gates / ms * 1e3,
+                              "ms_per_pass": ms / plan.n_passes,
+                              "GBps_per_pass": bytes_pass * plan.n_passes / ms / 1e6})
         hb.lib.hq_set_tuning(2, 0)
         # unfused reference point
-        plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(0, -1, 0, 0, 0))
+        plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(0, -1, 0, 0, 0, 0, -1))
         ms = timed(lambda: plan.run(st), warm=1, reps=1)
         emit({"what": "circuit_unfused", "ctype": ctype, "n": n, "gates": plan.n_gates, "passes": plan.n_passes,
               "ms": ms, "gate_applies_per_s": plan.n_gates / ms * 1e3,
