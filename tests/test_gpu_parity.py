@@ -126,7 +126,9 @@ def test_plan_variants_vs_oracle(hb, oracle, c_oracle, ctype):
         for nbuf in (1, 2):
             hb.lib.hq_set_tuning(nbuf, 0)
             for opts in (None, hb.PlanOptions(10, 3, 1, 0, 0), hb.PlanOptions(13, 5, 1, 0, 0),
-                         hb.PlanOptions(12, 5, 0, 0, 0), hb.PlanOptions(11, 1, 1, 3, 0)):
+                         hb.PlanOptions(12, 5, 0, 0, 0), hb.PlanOptions(11, 1, 1, 3, 0),
+                         hb.PlanOptions(12, 5, 1, 0, 0, 0, -1), hb.PlanOptions(12, 4, 1, 0, 0, 2, 0),
+                         hb.PlanOptions(13, 5, 1, 0, 0, 3, 24)):
                 plan = hb.Plan(lowered, n, ctype, opts)
                 st = hb.DeviceState(n, ctype).upload(psi)
                 plan.run(st)
