@@ -103,7 +103,7 @@ _proto("hq_plan_pass_info", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int
 _proto("hq_plan_pass_gates", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int)
 _proto("hq_plan_run", ctypes.c_int, _vp, _vp, _vp)
 _proto("hq_plan_run_range", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp)
-_proto("hq_set_tuning", ctypes.c_int, ctypes.c_int, ctypes.c_int)
+_proto("hq_set_tuning", ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int)
 _proto("hq_launch_count", ctypes.c_uint64)
 _proto("hq_launch_count_reset", None)
 

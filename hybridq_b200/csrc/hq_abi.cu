@@ -78,10 +78,25 @@ void fill_gate(hq::GateIn& g, const T* U, const unsigned* pos, unsigned k) {
   for (size_t i = 0; i < e; ++i) g.U[i] = std::complex<double>(double(U[2 * i]), double(U[2 * i + 1]));
 }
 
+int g_use_direct = 1;   // single k <= 2 gate passes go to the shared-memory-free kernel
+
 int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, int first, int last, void* stream) {
   for (int p = first; p < last; ++p) {
     const HqPassHeader& ph = plan.passes[size_t(p)].header;
     if (ph.n_gates == 0 && !ph.has_perm) continue;
+    if (g_use_direct && ph.n_gates == 1 && !ph.has_perm && ph.max_k <= 2 && plan.n_qubits >= ph.max_k + 1) {
+      // measured (profiles/): the direct kernel runs a lone 1-/2-qubit gate at copy bandwidth
+      HqGateDesc gd;
+      memcpy(&gd, plan.program.data() + ph.gates_off, sizeof(gd));
+      const unsigned L = ph.tile_bits - ph.n_high;
+      unsigned pos[4];
+      for (unsigned i = 0; i < gd.k; ++i) pos[i] = gd.tpos[i] < L ? gd.tpos[i] : ph.high_pos[gd.tpos[i] - L];
+      const int rc = hq::launch_direct_gate(plan.dtype, state, plan.n_qubits, plan.program.data() + gd.mat_off, pos,
+                                            gd.k, stream);
+      if (rc) return cuda_fail("direct gate launch", rc);
+      ++g_launches;
+      continue;
+    }
     const int rc = hq::launch_tile_pass(plan.dtype, state, plan.n_qubits, d_prog, ph, stream, 0);
     if (rc) return cuda_fail("tile pass launch", rc);
     ++g_launches;
@@ -497,8 +512,9 @@ int hq_plan_run(hq_plan* plan, void* state, void* stream) {
   return hq_plan_run_range(plan, state, 0, int(plan->plan.passes.size()), stream);
 }
 
-int hq_set_tuning(int nbuf, int ctas_per_sm) {
+int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct) {
   hq::set_tuning(nbuf, ctas_per_sm);
+  if (use_direct >= 0) g_use_direct = use_direct;
   return 0;
 }
 

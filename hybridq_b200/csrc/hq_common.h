@@ -30,7 +30,10 @@
 #define HQ_GATE_SMALL 0
 #define HQ_GATE_BIG 1
 
-struct HqGateDesc {        // 48 bytes, lives in the device program buffer
+#define HQ_MAX_PER_THREAD 16   // units per thread per tile = 2^(unit bits - 8) <= 16
+#define HQ_MAX_PASS_GATES 24   // kernel matrices per pass after merging
+
+struct HqGateDesc {        // 624 bytes, lives in the device program buffer (read through L1)
   uint32_t k;              // number of target bits
   uint32_t kind;           // HQ_GATE_SMALL / HQ_GATE_BIG
   uint32_t mat_off;        // byte offset of the matrix from the program base
@@ -40,9 +43,16 @@ struct HqGateDesc {        // 48 bytes, lives in the device program buffer
   uint8_t tpos[16];        // ascending LOCAL amplitude-bit positions of matrix bits 0..k-1
   uint8_t q[16];           // small: ordering of the non-target local UNIT bits (work-item bit b
                            //        -> unit bit q[b]); big: non-target local AMPLITUDE bits
+  // Register-path lane tables, precomputed by the planner so that the kernel does no bit
+  // scattering at all.  Work item w = tid + (it << 8) of a gate touches the units
+  //   slot(w, m) = tbl_thread[tid] ^ tbl_iter[it] ^ tbl_x[m],   m = 0 .. 2^KK - 1
+  // (already swizzled shared-memory slots; swz is GF(2)-linear so the XOR composes).
+  uint16_t tbl_thread[HQ_THREADS];
+  uint16_t tbl_iter[16];
+  uint16_t tbl_x[16];
 };
 
-struct HqPassHeader {      // passed to the kernel by value
+struct HqPassHeader {      // passed to the kernel by value (constant bank)
   uint32_t n_gates;
   uint32_t tile_bits;      // T, in amplitudes
   uint32_t n_high;         // h
@@ -55,7 +65,12 @@ struct HqPassHeader {      // passed to the kernel by value
   uint8_t perm[16];
   uint32_t max_k;          // largest k among the gates of the pass (selects the kernel variant)
   uint32_t reserved;
+  // Fill/drain addressing: local unit c = tid + (i << 8) lives at global unit
+  //   tile_base + off(tid) + iter_off[i]   and at shared-memory slot  swz(tid) ^ iter_swz[i]
+  // (off() deposits the bits of c at their global positions, so it splits over disjoint bits).
+  uint64_t iter_off[HQ_MAX_PER_THREAD];
+  uint32_t iter_swz[HQ_MAX_PER_THREAD];
 };
 
-static_assert(sizeof(HqGateDesc) == 48, "HqGateDesc layout");
-static_assert(sizeof(HqPassHeader) == 60, "HqPassHeader layout");
+static_assert(sizeof(HqGateDesc) == 624, "HqGateDesc layout");
+static_assert(sizeof(HqPassHeader) == 256, "HqPassHeader layout");

@@ -22,42 +22,52 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
   const int Tu = Tbits - V, Lu = Tbits - h - V;
   const uint32_t n_units = 1u << Tu;
   std::vector<Unit> tile(n_units);
-  std::vector<uint64_t> run_off(size_t(1) << h);
-  for (uint32_t r = 0; r < (1u << h); ++r) run_off[r] = hq::deposit(r, ph.high_pos, h) >> V;
-  std::vector<HqGateDesc> gd(ph.n_gates);
-  if (ph.n_gates) memcpy(gd.data(), prog + ph.gates_off, ph.n_gates * sizeof(HqGateDesc));
+  const HqGateDesc* gates = reinterpret_cast<const HqGateDesc*>(prog + ph.gates_off);
   const uint64_t n_tiles = uint64_t(1) << (n - ph.tile_bits);
   for (uint64_t t = 0; t < n_tiles; ++t) {
     const uint64_t base_unit = hq::tile_base(t, Tbits, h, ph.high_pos) >> V;
-    for (int tid = 0; tid < HQ_THREADS; ++tid)
-      for (uint32_t c = uint32_t(tid); c < n_units; c += HQ_THREADS)
-        tile[hq::swz(c)] = state[hq::unit_global(c, base_unit, run_off.data(), Lu)];
+    // fill, exactly as the kernel addresses it
+    for (int tid = 0; tid < HQ_THREADS; ++tid) {
+      const int npt = Tu > HQ_THREADS_LOG2 ? (1 << (Tu - HQ_THREADS_LOG2)) : (uint32_t(tid) < n_units ? 1 : 0);
+      const uint64_t off_t = hq::unit_offset(uint32_t(tid), Lu, V, ph.high_pos, h);
+      const uint32_t swz_t = hq::swz(uint32_t(tid));
+      for (int i = 0; i < npt; ++i) tile[swz_t ^ ph.iter_swz[i]] = state[base_unit + off_t + ph.iter_off[i]];
+    }
     for (uint32_t gi = 0; gi < ph.n_gates; ++gi) {
-      const HqGateDesc& g = gd[gi];
-      if (g.kind == HQ_GATE_SMALL) {
-        for (int tid = 0; tid < HQ_THREADS; ++tid) hq::gate_small_dispatch<4>(tile.data(), g, prog, Tu, tid);
+      const HqGateDesc* g = gates + gi;
+      if (g->k <= HQ_SMALL_K) {
+        const bool low = V == 1 && g->tpos[0] == 0;
+        for (int tid = 0; tid < HQ_THREADS; ++tid)
+          hq::gate_small_dispatch<4>(tile.data(), g, g->k, low, prog, g->mat_off, Tu, tid);
       } else {
-        const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + g.mat_off);
-        const int rounds = hq::big_rounds(Tbits, int(g.k));
+        const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + g->mat_off);
+        const int rounds = hq::big_rounds(Tbits, int(g->k));
         std::vector<hq::BigAcc<T>> acc(HQ_THREADS);
         for (int r = 0; r < rounds; ++r) {
           for (int tid = 0; tid < HQ_THREADS; ++tid)
-            hq::gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile.data()), g, Ut, Tbits, tid, r, acc[size_t(tid)]);
+            hq::gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile.data()), *g, Ut, Tbits, tid, r, acc[size_t(tid)]);
           for (int tid = 0; tid < HQ_THREADS; ++tid)
-            hq::gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile.data()), g, acc[size_t(tid)]);
+            hq::gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile.data()), *g, acc[size_t(tid)]);
         }
       }
     }
-    if (!ph.has_perm) {
-      for (uint32_t c = 0; c < n_units; ++c)
-        state[hq::unit_global(c, base_unit, run_off.data(), Lu)] = tile[hq::swz(c)];
-    } else {
-      const Cplx* amps = reinterpret_cast<const Cplx*>(tile.data());
-      for (uint32_t c = 0; c < n_units; ++c) {
-        Cplx o[1 << V];
-        for (uint32_t e = 0; e < (1u << V); ++e)
-          o[e] = amps[hq::amp_slot<T>(hq::perm_src((c << V) | e, ph.perm, Tbits))];
-        state[hq::unit_global(c, base_unit, run_off.data(), Lu)] = hq::make_unit(o);
+    const Cplx* amps = reinterpret_cast<const Cplx*>(tile.data());
+    for (int tid = 0; tid < HQ_THREADS; ++tid) {
+      const int npt = Tu > HQ_THREADS_LOG2 ? (1 << (Tu - HQ_THREADS_LOG2)) : (uint32_t(tid) < n_units ? 1 : 0);
+      const uint64_t off_t = hq::unit_offset(uint32_t(tid), Lu, V, ph.high_pos, h);
+      const uint32_t swz_t = hq::swz(uint32_t(tid));
+      for (int i = 0; i < npt; ++i) {
+        Unit out;
+        if (!ph.has_perm) {
+          out = tile[swz_t ^ ph.iter_swz[i]];
+        } else {
+          const uint32_t c = uint32_t(tid) + (uint32_t(i) << HQ_THREADS_LOG2);
+          Cplx o[1 << V];
+          for (uint32_t e = 0; e < (1u << V); ++e)
+            o[e] = amps[hq::amp_slot<T>(hq::perm_src((c << V) | e, ph.perm, Tbits))];
+          out = hq::make_unit(o);
+        }
+        state[base_unit + off_t + ph.iter_off[i]] = out;
       }
     }
   }

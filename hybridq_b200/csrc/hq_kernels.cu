@@ -50,20 +50,20 @@ __device__ __forceinline__ void st_stream(Unit* p, const Unit& v) {
 // KCLASS: 0 = passes whose gates all have k <= 2, 1 = k <= 3, 2 = k <= 4, 3 = anything (adds
 // the two-phase path); the narrower classes need far fewer registers.
 // ---------------------------------------------------------------------------------------
+// Fill: local unit c = tid + (i << 8) comes from global unit base + off_t + iter_off[i] and
+// goes to slot swz_t ^ iter_swz[i]; iter_* sit in the constant bank (kernel parameter).
 template <typename T>
 __device__ __forceinline__ void tile_fill(typename Traits<T>::Unit* tile,
-                                          const typename Traits<T>::Unit* __restrict__ state,
-                                          uint64_t base_unit, const uint64_t* run_off, int Lu,
-                                          uint32_t n_units, int tid) {
+                                          const typename Traits<T>::Unit* __restrict__ src,
+                                          const HqPassHeader& ph, uint32_t swz_t, int npt) {
 #pragma unroll 4
-  for (uint32_t c = tid; c < n_units; c += HQ_THREADS)
-    cp_async16(&tile[swz(c)], &state[unit_global(c, base_unit, run_off, Lu)]);
+  for (int i = 0; i < npt; ++i) cp_async16(&tile[swz_t ^ ph.iter_swz[i]], src + ph.iter_off[i]);
 }
 
 template <typename T, int KCLASS, int NBUF>
 __global__ void __launch_bounds__(HQ_THREADS, (KCLASS <= 1 ? 3 : 2))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
-               const HqPassHeader ph, const unsigned long long n_tiles) {
+               const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles) {
   typedef typename Traits<T>::Unit Unit;
   typedef typename Traits<T>::Cplx Cplx;
   const int V = Traits<T>::V;
@@ -77,64 +77,55 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
   const int Lu = Tbits - h - V;
   const uint32_t n_units = 1u << Tu;
   const uint32_t n_gates = ph.n_gates;
+  const int npt = Tu > HQ_THREADS_LOG2 ? (1 << (Tu - HQ_THREADS_LOG2)) : (uint32_t(tid) < n_units ? 1 : 0);
 
   Unit* bufs = reinterpret_cast<Unit*>(smem);
-  uint64_t* run_off = reinterpret_cast<uint64_t*>(smem + (size_t(16 * NBUF) << Tu));
-  HqGateDesc* gd = reinterpret_cast<HqGateDesc*>(run_off + (size_t(1) << h));
-  uint8_t* s_high = reinterpret_cast<uint8_t*>(gd + n_gates);
-  uint8_t* s_perm = s_high + 16;
+  const HqGateDesc* gates = reinterpret_cast<const HqGateDesc*>(prog + ph.gates_off);
 
-  if (tid < 16) {
-    s_high[tid] = ph.high_pos[tid];
-    s_perm[tid] = ph.perm[tid];
-  }
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(prog + ph.gates_off);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(gd);
-    const uint32_t words = n_gates * (sizeof(HqGateDesc) / 4);
-    for (uint32_t i = tid; i < words; i += HQ_THREADS) dst[i] = src[i];
-  }
-  __syncthreads();
-  for (uint32_t r = tid; r < (1u << h); r += HQ_THREADS) run_off[r] = deposit(r, s_high, h) >> V;
-  __syncthreads();
+  // per-thread constants of the fill/drain addressing
+  const uint64_t off_t = unit_offset(uint32_t(tid), Lu, V, ph.high_pos, h);
+  const uint32_t swz_t = swz(uint32_t(tid));
 
   unsigned long long t = blockIdx.x;
   int cur = 0;
   if (NBUF == 2 && t < n_tiles) {
-    tile_fill<T>(bufs, state, tile_base(t, Tbits, h, s_high) >> V, run_off, Lu, n_units, tid);
+    tile_fill<T>(bufs, state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t, ph, swz_t, npt);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
   for (; t < n_tiles; t += gridDim.x) {
-    const uint64_t base_unit = tile_base(t, Tbits, h, s_high) >> V;
+    Unit* gptr = state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t;
     Unit* tile = bufs + (size_t(cur) << Tu);
     if (NBUF == 2) {
       const unsigned long long tn = t + gridDim.x;
       if (tn < n_tiles) {
-        tile_fill<T>(bufs + (size_t(cur ^ 1) << Tu), state, tile_base(tn, Tbits, h, s_high) >> V, run_off, Lu,
-                     n_units, tid);
+        tile_fill<T>(bufs + (size_t(cur ^ 1) << Tu), state + (tile_base(tn, Tbits, h, ph.high_pos) >> V) + off_t,
+                     ph, swz_t, npt);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       } else {
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       }
     } else {
-      tile_fill<T>(tile, state, base_unit, run_off, Lu, n_units, tid);
+      tile_fill<T>(tile, gptr, ph, swz_t, npt);
       cp_async_wait_all();
     }
     __syncthreads();
 
     for (uint32_t gi = 0; gi < n_gates; ++gi) {
-      const HqGateDesc& g = gd[gi];
-      if (KCLASS < 3 || g.kind == HQ_GATE_SMALL) {
-        gate_small_dispatch<MAXK>(tile, g, prog, Tu, tid);
+      const HqGateDesc* g = gates + gi;
+      const uint32_t k = __ldg(&g->k);
+      const uint32_t mat_off = __ldg(&g->mat_off);
+      if (KCLASS < 3 || k <= HQ_SMALL_K) {
+        const bool low = V == 1 && __ldg(&g->tpos[0]) == 0;
+        gate_small_dispatch<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
       } else {
-        const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + g.mat_off);
-        const int rounds = big_rounds(Tbits, int(g.k));
+        const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + mat_off);
+        const int rounds = big_rounds(Tbits, int(k));
         for (int r = 0; r < rounds; ++r) {
           BigAcc<T> acc;
-          gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile), g, Ut, Tbits, tid, r, acc);
+          gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile), *g, Ut, Tbits, tid, r, acc);
           __syncthreads();
-          gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile), g, acc);
+          gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile), *g, acc);
         }
       }
       __syncthreads();
@@ -143,16 +134,16 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     // drain
     if (!ph.has_perm) {
 #pragma unroll 4
-      for (uint32_t c = tid; c < n_units; c += HQ_THREADS)
-        st_stream(&state[unit_global(c, base_unit, run_off, Lu)], tile[swz(c)]);
+      for (int i = 0; i < npt; ++i) st_stream(gptr + ph.iter_off[i], tile[swz_t ^ ph.iter_swz[i]]);
     } else {
       const Cplx* amps = reinterpret_cast<const Cplx*>(tile);
-      for (uint32_t c = tid; c < n_units; c += HQ_THREADS) {
+      for (int i = 0; i < npt; ++i) {
+        const uint32_t c = uint32_t(tid) + (uint32_t(i) << HQ_THREADS_LOG2);
         Cplx o[1 << V];
 #pragma unroll
         for (uint32_t e = 0; e < (1u << V); ++e)
-          o[e] = amps[amp_slot<T>(perm_src((c << V) | e, s_perm, Tbits))];
-        st_stream(&state[unit_global(c, base_unit, run_off, Lu)], make_unit(o));
+          o[e] = amps[amp_slot<T>(perm_src((c << V) | e, ph.perm, Tbits))];
+        st_stream(gptr + ph.iter_off[i], make_unit(o));
       }
     }
     __syncthreads();
@@ -160,17 +151,17 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
   }
 }
 
-static int g_tune_nbuf = 2;
+static int g_tune_nbuf = 0;          // 0 = auto: double-buffer when it costs no resident CTA
 static int g_tune_ctas_per_sm = 0;
 void set_tuning(int nbuf, int ctas_per_sm) {
-  if (nbuf == 1 || nbuf == 2) g_tune_nbuf = nbuf;
+  if (nbuf >= 0 && nbuf <= 2) g_tune_nbuf = nbuf;
   if (ctas_per_sm >= 0) g_tune_ctas_per_sm = ctas_per_sm;
 }
 
-size_t tile_pass_smem_bytes(const HqPassHeader& ph, int dtype) {
+size_t tile_pass_smem_bytes(const HqPassHeader& ph, int dtype, int nbuf) {
   const int V = dtype == HQ_DTYPE_C64 ? 1 : 0;
   const int Tu = int(ph.tile_bits) - V;
-  return (size_t(16 * g_tune_nbuf) << Tu) + (size_t(8) << ph.n_high) + size_t(ph.n_gates) * sizeof(HqGateDesc) + 32;
+  return size_t(16 * nbuf) << Tu;
 }
 
 static DeviceInfo g_info[64];
@@ -192,30 +183,62 @@ int device_info(DeviceInfo* out) {
   return 0;
 }
 
+// resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached)
 template <typename T, int KCLASS, int NBUF>
-static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
-                               cudaStream_t stream, int grid_override, size_t smem, const DeviceInfo& di, int dev) {
+static int variant_occupancy(size_t smem, const DeviceInfo& di, int dev, int* per_sm_out) {
   static bool attr_set[64];
+  static int cache[64][HQ_MAX_UNIT_BITS + 2];
   auto kern = hq_tile_kernel<T, KCLASS, NBUF>;
   if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
     if (e != cudaSuccess) return int(e);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return int(e);
+    for (int i = 0; i < HQ_MAX_UNIT_BITS + 2; ++i) cache[dev][i] = -1;
     attr_set[dev] = true;
   }
+  int slot = 0;
+  while ((size_t(16 * NBUF) << slot) < smem && slot < HQ_MAX_UNIT_BITS + 1) ++slot;
+  if (cache[dev][slot] < 0) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HQ_THREADS, smem);
+    if (e != cudaSuccess) return int(e);
+    cache[dev][slot] = per_sm;
+  }
+  *per_sm_out = cache[dev][slot];
+  return 0;
+}
+
+template <typename T, int KCLASS, int NBUF>
+static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                               cudaStream_t stream, int grid_override, size_t smem, const DeviceInfo& di, int per_sm) {
   const unsigned long long n_tiles = 1ull << (n_qubits - ph.tile_bits);
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HQ_THREADS, smem);
-  if (e != cudaSuccess) return int(e);
   if (per_sm < 1) return int(cudaErrorLaunchOutOfResources);
   if (g_tune_ctas_per_sm > 0 && g_tune_ctas_per_sm < per_sm) per_sm = g_tune_ctas_per_sm;
   unsigned long long grid = (unsigned long long)di.sm_count * (unsigned long long)per_sm;
   if (grid_override > 0) grid = (unsigned long long)grid_override;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<unsigned(grid), HQ_THREADS, smem, stream>>>(reinterpret_cast<typename Traits<T>::Unit*>(state), prog, ph,
-                                                     n_tiles);
+  hq_tile_kernel<T, KCLASS, NBUF><<<unsigned(grid), HQ_THREADS, smem, stream>>>(
+      reinterpret_cast<typename Traits<T>::Unit*>(state), prog, ph, n_tiles);
   return int(cudaGetLastError());
+}
+
+template <typename T, int KCLASS>
+static int launch_tile_class(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                             cudaStream_t stream, int grid_override, const DeviceInfo& di, int dev) {
+  const int dtype = Traits<T>::V == 1 ? HQ_DTYPE_C64 : HQ_DTYPE_C128;
+  const size_t smem1 = tile_pass_smem_bytes(ph, dtype, 1), smem2 = tile_pass_smem_bytes(ph, dtype, 2);
+  int occ1 = 0, occ2 = 0;
+  int rc = variant_occupancy<T, KCLASS, 1>(smem1, di, dev, &occ1);
+  if (rc) return rc;
+  bool two = false;
+  if (g_tune_nbuf != 1 && smem2 <= size_t(di.max_smem_optin)) {
+    rc = variant_occupancy<T, KCLASS, 2>(smem2, di, dev, &occ2);
+    if (rc) return rc;
+    two = g_tune_nbuf == 2 ? occ2 >= 1 : occ2 >= occ1;
+  }
+  if (two) return launch_tile_variant<T, KCLASS, 2>(state, n_qubits, prog, ph, stream, grid_override, smem2, di, occ2);
+  return launch_tile_variant<T, KCLASS, 1>(state, n_qubits, prog, ph, stream, grid_override, smem1, di, occ1);
 }
 
 template <typename T>
@@ -228,18 +251,14 @@ static int launch_tile_pass_t(void* state, unsigned n_qubits, const unsigned cha
   int dev = 0;
   cudaGetDevice(&dev);
   if (ph.tile_bits > n_qubits) return int(cudaErrorInvalidValue);
-  const size_t smem = tile_pass_smem_bytes(ph, dtype);
-  if (smem > size_t(di.max_smem_optin)) return int(cudaErrorInvalidValue);
+  if (tile_pass_smem_bytes(ph, dtype, 1) > size_t(di.max_smem_optin)) return int(cudaErrorInvalidValue);
   const int kclass = ph.max_k <= 2 ? 0 : (ph.max_k <= 3 ? 1 : (ph.max_k <= 4 ? 2 : 3));
-  const bool two = g_tune_nbuf == 2;
-#define HQ_LAUNCH(KC, NB) launch_tile_variant<T, KC, NB>(state, n_qubits, prog, ph, stream, grid_override, smem, di, dev)
   switch (kclass) {
-    case 0: return two ? HQ_LAUNCH(0, 2) : HQ_LAUNCH(0, 1);
-    case 1: return two ? HQ_LAUNCH(1, 2) : HQ_LAUNCH(1, 1);
-    case 2: return two ? HQ_LAUNCH(2, 2) : HQ_LAUNCH(2, 1);
-    default: return two ? HQ_LAUNCH(3, 2) : HQ_LAUNCH(3, 1);
+    case 0: return launch_tile_class<T, 0>(state, n_qubits, prog, ph, stream, grid_override, di, dev);
+    case 1: return launch_tile_class<T, 1>(state, n_qubits, prog, ph, stream, grid_override, di, dev);
+    case 2: return launch_tile_class<T, 2>(state, n_qubits, prog, ph, stream, grid_override, di, dev);
+    default: return launch_tile_class<T, 3>(state, n_qubits, prog, ph, stream, grid_override, di, dev);
   }
-#undef HQ_LAUNCH
 }
 
 int launch_tile_pass(int dtype, void* state, unsigned n_qubits, const unsigned char* prog,

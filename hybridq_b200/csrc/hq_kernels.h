@@ -20,8 +20,9 @@ int device_info(DeviceInfo* out);
 //   launches   if non-null, incremented by the number of kernel launches issued
 int launch_tile_pass(int dtype, void* state, unsigned n_qubits, const unsigned char* prog,
                      const HqPassHeader& ph, void* stream, int grid_override);
-size_t tile_pass_smem_bytes(const HqPassHeader& ph, int dtype);
-// nbuf: 1 = single-buffered tiles, 2 = next tile prefetched while the current one is processed;
+size_t tile_pass_smem_bytes(const HqPassHeader& ph, int dtype, int nbuf);
+// nbuf: 0 = auto (double-buffer when it costs no resident CTA), 1 = single-buffered tiles,
+// 2 = next tile prefetched while the current one is processed;
 // ctas_per_sm: cap on resident CTAs per SM (0 = occupancy limit)
 void set_tuning(int nbuf, int ctas_per_sm);
 

@@ -1,5 +1,6 @@
 // hq_plan.cpp -- see hq_plan.h.
 #include "hq_plan.h"
+#include "hq_tile.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -11,7 +12,7 @@ int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 4; }  /
 
 namespace {
 
-const int kMaxGatesPerPass = 48;
+const int kMaxGatesPerPass = 48;   // gate-applies per pass before merging
 
 int vbits(int dtype) { return dtype == HQ_DTYPE_C64 ? 1 : 0; }
 int max_tile_bits(int dtype) { return HQ_MAX_UNIT_BITS + vbits(dtype); }
@@ -76,6 +77,35 @@ void make_tile(const std::vector<unsigned>& bits_sorted, int T, int L, unsigned 
   ph.tile_bits = uint32_t(L + int(high.size()));
   ph.n_high = uint32_t(high.size());
   for (size_t i = 0; i < high.size(); ++i) ph.high_pos[i] = uint8_t(high[i]);
+}
+
+// Fill/drain addressing tables of a pass (see HqPassHeader).
+void make_iter_tables(HqPassHeader& ph, int V) {
+  const int Tu = int(ph.tile_bits) - V;
+  const int Lu = int(ph.tile_bits) - int(ph.n_high) - V;
+  const int npt = Tu > HQ_THREADS_LOG2 ? (1 << (Tu - HQ_THREADS_LOG2)) : 1;
+  for (int i = 0; i < HQ_MAX_PER_THREAD; ++i) {
+    const uint32_t c = i < npt ? (uint32_t(i) << HQ_THREADS_LOG2) : 0u;
+    ph.iter_off[i] = i < npt && Tu > HQ_THREADS_LOG2 ? unit_offset(c, Lu, V, ph.high_pos, int(ph.n_high)) : 0;
+    ph.iter_swz[i] = i < npt && Tu > HQ_THREADS_LOG2 ? swz(c) : 0u;
+  }
+}
+
+// Lane tables of a register-path gate (see HqGateDesc).
+void make_lane_tables(HqGateDesc& gd, int Tu, int V) {
+  const bool low = V == 1 && gd.tpos[0] == 0;
+  const int KK = int(gd.k) - (low ? 1 : 0);
+  const int nq = Tu - KK;
+  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
+  for (int t = 0; t < HQ_THREADS; ++t)
+    gd.tbl_thread[t] = uint16_t(swz(scatter_bits(uint32_t(t) & ((1u << tb) - 1u), gd.q, 0, tb)));
+  const int niter = 1 << (nq - tb);
+  for (int it = 0; it < 16; ++it)
+    gd.tbl_iter[it] = it < niter ? uint16_t(swz(scatter_bits(uint32_t(it), gd.q, tb, nq))) : uint16_t(0);
+  uint8_t upos[16] = {0};
+  for (int i = 0; i < KK; ++i) upos[i] = uint8_t(gd.tpos[i + (low ? 1 : 0)] - V);
+  for (int m = 0; m < 16; ++m)
+    gd.tbl_x[m] = m < (1 << KK) ? uint16_t(swz(uint32_t(deposit(uint32_t(m), upos, KK)))) : uint16_t(0);
 }
 
 int local_bit(const HqPassHeader& ph, unsigned global_bit) {
@@ -318,6 +348,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     int L = choose_run_bits(d.bits, T, d.ids.size() > 1 ? fuse_min_run : hard_min_run);
     if (L < 0) { plan.error = "internal: pass does not fit"; return 1; }
     make_tile(d.bits, T, L, n, pi.header);
+    make_iter_tables(pi.header, V);
     pi.header.n_gates = uint32_t(merged[di].size());
     pi.header.gates_off = uint32_t(gate_cursor * sizeof(HqGateDesc));
     const int Tbits = int(pi.header.tile_bits);
@@ -349,6 +380,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       }
       gd.n_free = uint32_t(free_bits.size());
       for (size_t i = 0; i < free_bits.size() && i < 16; ++i) gd.q[i] = uint8_t(free_bits[i]);
+      if (gd.kind == HQ_GATE_SMALL) make_lane_tables(gd, Tu, V);
       memcpy(plan.program.data() + gate_cursor * sizeof(HqGateDesc), &gd, sizeof(gd));
       if (dtype == HQ_DTYPE_C64)
         write_matrix<float>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
@@ -418,6 +450,7 @@ int plan_build_bitperm(Plan& plan, int dtype, unsigned n, const std::vector<unsi
     PassInfo pi;
     const int L = choose_run_bits(bits, T, (e - s) > 1 ? min_run : hard_min_run);
     make_tile(bits, T, L, n, pi.header);
+    make_iter_tables(pi.header, V);
     const int Tbits = int(pi.header.tile_bits);
     // compose: total[i] = p1[p2[...pk[i]]] where stage r has new bit a <- old bit b and vice versa
     std::vector<unsigned> total;

@@ -32,6 +32,7 @@
 #define HQ_LDG(p) (*(p))
 #define HQ_UNROLL
 #define HQ_NOUNROLL
+#define HQ_NOUNROLL
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
@@ -81,47 +82,58 @@ HQ_HD uint64_t tile_base(uint64_t t, int tile_bits, int n_high, const uint8_t* h
 // ---------------------------------------------------------------------------------------
 // complex helpers
 // ---------------------------------------------------------------------------------------
+HQ_DEV float hq_fma(float a, float b, float c) {
+#ifdef __CUDACC__
+  return __fmaf_rn(a, b, c);
+#else
+  return a * b + c;
+#endif
+}
+HQ_DEV double hq_fma(double a, double b, double c) {
+#ifdef __CUDACC__
+  return __fma_rn(a, b, c);
+#else
+  return a * b + c;
+#endif
+}
+
+// (ar, ai) += (ur, ui) * (xr, xi) as exactly four FMAs (the arithmetic of U.h:93-94)
 template <typename R>
 HQ_DEV void cmac(R& ar, R& ai, R ur, R ui, R xr, R xi) {
-  // same operation order as the reference inner loop (U.h:93-94)
-  ar += ur * xr - ui * xi;
-  ai += ur * xi + ui * xr;
+  ar = hq_fma(ur, xr, ar);
+  ar = hq_fma(-ui, xi, ar);
+  ai = hq_fma(ur, xi, ai);
+  ai = hq_fma(ui, xr, ai);
 }
 
-// XOR of s[i] over the set bits of m.
-template <int KK>
-HQ_DEV uint32_t xoff(uint32_t m, const uint32_t* s) {
-  uint32_t o = 0;
-  HQ_UNROLL
-  for (int i = 0; i < KK; ++i) o ^= ((m >> i) & 1u) ? s[i] : 0u;
-  return o;
-}
-
-// Work item w (bits [0, n_free)) -> local unit/amp index with zeros at the target bits.
-// The low `tb` bits come from `lo` (the thread id), the rest from `hi` (the iteration).
-HQ_DEV uint32_t scatter_bits(uint32_t w, const uint8_t* q, int from, int to) {
+// Work item w (bits [0, n_free)) -> local unit/amp index with zeros at the target bits
+// (used by the planner for the lane tables and by the two-phase path).
+HQ_HD uint32_t scatter_bits(uint32_t w, const uint8_t* q, int from, int to) {
   uint32_t u = 0;
   for (int b = from; b < to; ++b) u |= ((w >> (b - from)) & 1u) << q[b];
   return u;
 }
 
 // ---------------------------------------------------------------------------------------
-// register path, complex64, no target on amplitude bit 0: KK unit-level target bits,
-// every thread handles two groups at once (the even and the odd amplitude of its units).
+// register path: the slot of unit m of work item w = tid + (it << 8) is
+//   tbl_thread[tid] ^ tbl_iter[it] ^ tbl_x[m]      (see HqGateDesc)
+// GateIO loads / stores the units of one work item.
 // ---------------------------------------------------------------------------------------
+
+// complex64, no target on amplitude bit 0: KK unit-level target bits, every thread handles two
+// groups at once (the even and the odd amplitude of its units).
 template <int KK>
-HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc& g, const float2* __restrict__ U,
+HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc* __restrict__ g, const float2* __restrict__ U,
                            int Tu, int tid) {
   const int DIM = 1 << KK;
   const int nq = Tu - KK;
   const uint32_t nwork = 1u << nq;
   if (uint32_t(tid) >= nwork) return;
-  uint32_t s[KK > 0 ? KK : 1];
+  const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
+  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  uint32_t xo[DIM];
   HQ_UNROLL
-  for (int i = 0; i < KK; ++i) s[i] = swz(1u << (g.tpos[i] - 1));
-  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
-  const uint32_t ut = scatter_bits(uint32_t(tid), g.q, 0, tb);
-  const uint32_t niter = nwork >> tb;
+  for (int m = 0; m < DIM; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
 
   float2 Ur[KK <= 2 ? DIM * DIM : 1];
   if (KK <= 2) {
@@ -131,10 +143,10 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc& g, const float2* __re
 
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = swz(ut | scatter_bits(it, g.q, tb, nq));
+    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
     float4 in[DIM];
     HQ_UNROLL
-    for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xoff<KK>(m, s)];
+    for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xo[m]];
     if (KK <= 2) {
       HQ_UNROLL
       for (int i = 0; i < DIM; ++i) {
@@ -145,7 +157,7 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc& g, const float2* __re
           cmac(a0r, a0i, u.x, u.y, in[j].x, in[j].y);
           cmac(a1r, a1i, u.x, u.y, in[j].z, in[j].w);
         }
-        tile[sb ^ xoff<KK>(i, s)] = make_float4(a0r, a0i, a1r, a1i);
+        tile[sb ^ xo[i]] = make_float4(a0r, a0i, a1r, a1i);
       }
     } else {
       HQ_NOUNROLL
@@ -160,30 +172,27 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc& g, const float2* __re
           cmac(a0r, a0i, u.z, u.w, in[j + 1].x, in[j + 1].y);
           cmac(a1r, a1i, u.z, u.w, in[j + 1].z, in[j + 1].w);
         }
-        tile[sb ^ xoff<KK>(uint32_t(i), s)] = make_float4(a0r, a0i, a1r, a1i);
+        tile[sb ^ uint32_t(HQ_LDG(&g->tbl_x[i]))] = make_float4(a0r, a0i, a1r, a1i);
       }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// register path, complex64, matrix bit 0 sits on amplitude bit 0 (inside the unit):
-// K = KK + 1 matrix bits, one group per thread, amplitude m = unit (m >> 1) half (m & 1).
-// ---------------------------------------------------------------------------------------
+// complex64, matrix bit 0 sits on amplitude bit 0 (inside the unit): K = KK + 1 matrix bits,
+// one group per thread, amplitude m = unit (m >> 1) half (m & 1).
 template <int KK>
-HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc& g, const float2* __restrict__ U,
+HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc* __restrict__ g, const float2* __restrict__ U,
                                int Tu, int tid) {
   const int UD = 1 << KK;        // units per group
   const int DIM = 2 << KK;       // amplitudes per group
   const int nq = Tu - KK;
   const uint32_t nwork = 1u << nq;
   if (uint32_t(tid) >= nwork) return;
-  uint32_t s[KK > 0 ? KK : 1];
+  const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
+  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  uint32_t xo[UD];
   HQ_UNROLL
-  for (int i = 0; i < KK; ++i) s[i] = swz(1u << (g.tpos[i + 1] - 1));
-  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
-  const uint32_t ut = scatter_bits(uint32_t(tid), g.q, 0, tb);
-  const uint32_t niter = nwork >> tb;
+  for (int m = 0; m < UD; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
 
   float2 Ur[KK <= 1 ? DIM * DIM : 1];
   if (KK <= 1) {
@@ -193,10 +202,10 @@ HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc& g, const float2* 
 
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = swz(ut | scatter_bits(it, g.q, tb, nq));
+    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
     float4 in[UD];
     HQ_UNROLL
-    for (int m = 0; m < UD; ++m) in[m] = tile[sb ^ xoff<KK>(m, s)];
+    for (int m = 0; m < UD; ++m) in[m] = tile[sb ^ xo[m]];
     if (KK <= 1) {
       HQ_UNROLL
       for (int iu = 0; iu < UD; ++iu) {
@@ -210,7 +219,7 @@ HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc& g, const float2* 
           cmac(a1r, a1i, u10.x, u10.y, in[ju].x, in[ju].y);
           cmac(a1r, a1i, u11.x, u11.y, in[ju].z, in[ju].w);
         }
-        tile[sb ^ xoff<KK>(iu, s)] = make_float4(a0r, a0i, a1r, a1i);
+        tile[sb ^ xo[iu]] = make_float4(a0r, a0i, a1r, a1i);
       }
     } else {
       HQ_NOUNROLL
@@ -227,28 +236,25 @@ HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc& g, const float2* 
           cmac(a1r, a1i, ub.x, ub.y, in[ju].x, in[ju].y);
           cmac(a1r, a1i, ub.z, ub.w, in[ju].z, in[ju].w);
         }
-        tile[sb ^ xoff<KK>(uint32_t(iu), s)] = make_float4(a0r, a0i, a1r, a1i);
+        tile[sb ^ uint32_t(HQ_LDG(&g->tbl_x[iu]))] = make_float4(a0r, a0i, a1r, a1i);
       }
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// register path, complex128: unit = amplitude, one group per thread.
-// ---------------------------------------------------------------------------------------
+// complex128: unit = amplitude, one group per thread.
 template <int KK>
-HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc& g, const double2* __restrict__ U,
+HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc* __restrict__ g, const double2* __restrict__ U,
                            int Tu, int tid) {
   const int DIM = 1 << KK;
   const int nq = Tu - KK;
   const uint32_t nwork = 1u << nq;
   if (uint32_t(tid) >= nwork) return;
-  uint32_t s[KK > 0 ? KK : 1];
+  const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
+  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  uint32_t xo[DIM];
   HQ_UNROLL
-  for (int i = 0; i < KK; ++i) s[i] = swz(1u << g.tpos[i]);
-  const int tb = nq < HQ_THREADS_LOG2 ? nq : HQ_THREADS_LOG2;
-  const uint32_t ut = scatter_bits(uint32_t(tid), g.q, 0, tb);
-  const uint32_t niter = nwork >> tb;
+  for (int m = 0; m < DIM; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
 
   double2 Ur[KK <= 1 ? DIM * DIM : 1];
   if (KK <= 1) {
@@ -258,17 +264,17 @@ HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc& g, const double2* __
 
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = swz(ut | scatter_bits(it, g.q, tb, nq));
+    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
     double2 in[DIM];
     HQ_UNROLL
-    for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xoff<KK>(m, s)];
+    for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xo[m]];
     if (KK <= 1) {
       HQ_UNROLL
       for (int i = 0; i < DIM; ++i) {
         double ar = 0., ai = 0.;
         HQ_UNROLL
         for (int j = 0; j < DIM; ++j) cmac(ar, ai, Ur[i * DIM + j].x, Ur[i * DIM + j].y, in[j].x, in[j].y);
-        tile[sb ^ xoff<KK>(i, s)] = make_double2(ar, ai);
+        tile[sb ^ xo[i]] = make_double2(ar, ai);
       }
     } else {
       HQ_NOUNROLL
@@ -280,7 +286,7 @@ HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc& g, const double2* __
           const double2 u = HQ_LDG(&row[j]);
           cmac(ar, ai, u.x, u.y, in[j].x, in[j].y);
         }
-        tile[sb ^ xoff<KK>(uint32_t(i), s)] = make_double2(ar, ai);
+        tile[sb ^ uint32_t(HQ_LDG(&g->tbl_x[i]))] = make_double2(ar, ai);
       }
     }
   }
@@ -368,12 +374,11 @@ HQ_DEV void gate_big_phaseB(typename Traits<T>::Cplx* tile, const HqGateDesc& g,
 // MAXK prunes the switch so that a pass made of small gates only is compiled with few
 // registers (the kernel is instantiated per gate class, see hq_kernels.cu).
 template <int MAXK>
-HQ_DEV void gate_small_dispatch(float4* tile, const HqGateDesc& g, const unsigned char* prog,
-                                int Tu, int tid) {
-  const float2* U = reinterpret_cast<const float2*>(prog + g.mat_off);
-  const bool low = g.tpos[0] == 0;
+HQ_DEV void gate_small_dispatch(float4* tile, const HqGateDesc* g, uint32_t k, bool low,
+                                const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
+  const float2* U = reinterpret_cast<const float2*>(prog + mat_off);
   if (!low) {
-    switch (g.k) {
+    switch (k) {
       case 1: gate_small_f32<1>(tile, g, U, Tu, tid); break;
       case 2: gate_small_f32<2>(tile, g, U, Tu, tid); break;
       case 3: if (MAXK >= 3) gate_small_f32<3>(tile, g, U, Tu, tid); break;
@@ -381,7 +386,7 @@ HQ_DEV void gate_small_dispatch(float4* tile, const HqGateDesc& g, const unsigne
       default: break;
     }
   } else {
-    switch (g.k) {
+    switch (k) {
       case 1: gate_small_f32_low<0>(tile, g, U, Tu, tid); break;
       case 2: gate_small_f32_low<1>(tile, g, U, Tu, tid); break;
       case 3: if (MAXK >= 3) gate_small_f32_low<2>(tile, g, U, Tu, tid); break;
@@ -392,10 +397,10 @@ HQ_DEV void gate_small_dispatch(float4* tile, const HqGateDesc& g, const unsigne
 }
 
 template <int MAXK>
-HQ_DEV void gate_small_dispatch(double2* tile, const HqGateDesc& g, const unsigned char* prog,
-                                int Tu, int tid) {
-  const double2* U = reinterpret_cast<const double2*>(prog + g.mat_off);
-  switch (g.k) {
+HQ_DEV void gate_small_dispatch(double2* tile, const HqGateDesc* g, uint32_t k, bool /*low*/,
+                                const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
+  const double2* U = reinterpret_cast<const double2*>(prog + mat_off);
+  switch (k) {
     case 1: gate_small_f64<1>(tile, g, U, Tu, tid); break;
     case 2: gate_small_f64<2>(tile, g, U, Tu, tid); break;
     case 3: if (MAXK >= 3) gate_small_f64<3>(tile, g, U, Tu, tid); break;
@@ -408,9 +413,10 @@ HQ_DEV void gate_small_dispatch(double2* tile, const HqGateDesc& g, const unsign
 // tile fill / drain address math (the copies themselves are in the kernel / the emulator)
 // ---------------------------------------------------------------------------------------
 // local unit c of tile -> global unit index, given the tile's first unit and the run table.
-// run_off[r] = offset (in units) of run r from the tile's first unit.
-HQ_DEV uint64_t unit_global(uint32_t c, uint64_t base_unit, const uint64_t* run_off, int Lu) {
-  return base_unit + run_off[c >> Lu] + (c & ((1u << Lu) - 1u));
+// Offset (in units) of local unit c from the tile's first unit: the low Lu bits stay, the
+// bits above go to the tile's high positions.  Linear over disjoint bit sets.
+HQ_HD uint64_t unit_offset(uint32_t c, int Lu, int V, const uint8_t* high_pos, int n_high) {
+  return (deposit(c >> Lu, high_pos, n_high) >> V) + (c & ((1u << Lu) - 1u));
 }
 
 HQ_DEV float4 make_unit(const float2* a) { return make_float4(a[0].x, a[0].y, a[1].x, a[1].y); }

@@ -153,10 +153,12 @@ int hq_plan_run(hq_plan* plan, void* state, void* stream);
 /* launch passes [first, last) only */
 int hq_plan_run_range(hq_plan* plan, void* state, int first, int last, void* stream);
 
-/* measurement knobs of the tile kernel: nbuf = 1 (single-buffered tiles) or 2 (the next tile is
- * prefetched while the current one is processed; default); ctas_per_sm = cap on resident CTAs
- * per SM (0 = occupancy limit; default) */
-int hq_set_tuning(int nbuf, int ctas_per_sm);
+/* measurement knobs of the tile kernel: nbuf = 0 (auto, default: prefetch the next tile while the
+ * current one is processed whenever the second buffer costs no resident CTA), 1 (single-buffered)
+ * or 2 (always double-buffered); ctas_per_sm = cap on resident CTAs per SM (0 = occupancy limit);
+ * use_direct = 1 (default): a pass holding one k <= 2 gate runs on the shared-memory-free kernel.
+ * Negative values leave a knob unchanged. */
+int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct);
 
 /* counters: kernels launched by this library in this process since the last reset */
 uint64_t hq_launch_count(void);

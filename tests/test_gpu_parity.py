@@ -102,9 +102,12 @@ def test_device_apply_every_k_any_bits(hb, oracle, c_oracle, ctype):
             planes = oracle.split_state(psi)
             assert c_oracle.apply_U(planes[0], planes[1], U, pos) == 0
             ref = c_oracle.to_complex(planes[0], planes[1])
-            st = hb.DeviceState(n, ctype).upload(psi)
-            out = st.apply(U, pos).download()
-            assert np.abs(out - ref).max() <= TOL[ctype], (k, pos)
+            for use_direct in (1, 0):      # lone k <= 2 gates: direct kernel (default) and tile kernel
+                hb.lib.hq_set_tuning(-1, -1, use_direct)
+                st = hb.DeviceState(n, ctype).upload(psi)
+                out = st.apply(U, pos).download()
+                assert np.abs(out - ref).max() <= TOL[ctype], (k, pos, use_direct)
+            hb.lib.hq_set_tuning(-1, -1, 1)
             if k <= 3:
                 out = hb.DeviceState(n, ctype).upload(psi).apply(U, pos, direct=True).download()
                 assert np.abs(out - ref).max() <= TOL[ctype], ("direct", k, pos)
@@ -124,7 +127,7 @@ def test_plan_variants_vs_oracle(hb, oracle, c_oracle, ctype):
     ref = oracle.evolve_oracle(psi, [(U.astype(ctype), p) for U, p in lowered], c_oracle)
     try:
         for nbuf in (1, 2):
-            hb.lib.hq_set_tuning(nbuf, 0)
+            hb.lib.hq_set_tuning(nbuf, 0, -1)
             for opts in (None, hb.PlanOptions(10, 3, 1, 0, 0), hb.PlanOptions(13, 5, 1, 0, 0),
                          hb.PlanOptions(12, 5, 0, 0, 0), hb.PlanOptions(11, 1, 1, 3, 0),
                          hb.PlanOptions(12, 5, 1, 0, 0, 0, -1), hb.PlanOptions(12, 4, 1, 0, 0, 2, 0),
@@ -136,7 +139,7 @@ def test_plan_variants_vs_oracle(hb, oracle, c_oracle, ctype):
                 assert plan.n_gates == len(lowered)
                 assert np.abs(out - ref).max() <= TOL[ctype], (nbuf, opts and opts.tile_bits)
     finally:
-        hb.lib.hq_set_tuning(2, 0)
+        hb.lib.hq_set_tuning(0, 0, 1)
 
 
 def test_simulate_golden(hb, golden):

@@ -81,7 +81,7 @@ def main():
                 for T in tiles:
                     for nbuf in (1, 2):
                         for cps in (0,):
-                            hb.lib.hq_set_tuning(nbuf, cps)
+                            hb.lib.hq_set_tuning(nbuf, cps, 0)
                             try:
                                 plan = hb.Plan([(U, pos)], n, ctype, hb.PlanOptions(T, -1, 0, 0, 0))
                                 ms = timed(lambda: plan.run(st))
@@ -93,7 +93,7 @@ def main():
                             emit({"what": "single_gate", "kernel": "tile", "ctype": ctype, "n": n, "k": k, "pos": pos,
                                   "T": T, "nbuf": nbuf, "ctas_per_sm": cps, "n_high": info["n_high"], "ms": ms,
                                   "GBps": bytes_pass / ms / 1e6})
-        hb.lib.hq_set_tuning(2, 0)
+        hb.lib.hq_set_tuning(0, 0, 1)
 
         # whole circuits: planner options
         gates = matching_circuit(n, depth=20, seed=n)
@@ -103,7 +103,7 @@ def main():
             for min_run in (4, 5):
                 for merge in (0, 2, 3, 4):
                     for nbuf in (1, 2):
-                        hb.lib.hq_set_tuning(nbuf, 0)
+                        hb.lib.hq_set_tuning(nbuf, 0, -1)
                         try:
                             plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(T, min_run, 1, 0, 0, merge, -1))
                             ms = timed(lambda: plan.run(st), warm=1, reps=2)
@@ -116,7 +116,7 @@ def main():
                               "passes": plan.n_passes, "ms": ms, "gate_applies_per_s": plan.n_gates / ms * 1e3,
                               "ms_per_pass": ms / plan.n_passes,
                               "GBps_per_pass": bytes_pass * plan.n_passes / ms / 1e6})
-        hb.lib.hq_set_tuning(2, 0)
+        hb.lib.hq_set_tuning(0, 0, 1)
         # unfused reference point
         plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(0, -1, 0, 0, 0, 0, -1))
         ms = timed(lambda: plan.run(st), warm=1, reps=1)
