@@ -469,6 +469,17 @@ void hq_plan_destroy(hq_plan* plan) {
 int hq_plan_num_passes(const hq_plan* plan) { return plan ? int(plan->plan.passes.size()) : -1; }
 int hq_plan_num_gates(const hq_plan* plan) { return plan ? int(plan->plan.n_gates) : -1; }
 int hq_plan_num_kernel_gates(const hq_plan* plan) { return plan ? int(plan->plan.n_kernel_gates) : -1; }
+double hq_plan_flops(const hq_plan* plan) {
+  if (!plan) return -1.0;
+  double f = 0;
+  for (const hq::PassInfo& pi : plan->plan.passes)
+    for (uint32_t g = 0; g < pi.header.n_gates; ++g) {
+      HqGateDesc gd;
+      memcpy(&gd, plan->plan.program.data() + pi.header.gates_off + size_t(g) * sizeof(HqGateDesc), sizeof(gd));
+      f += 8.0 * double(1u << gd.k) * std::ldexp(1.0, int(plan->plan.n_qubits));
+    }
+  return f;
+}
 
 int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len) {
   if (!plan || pass < 0 || pass >= int(plan->plan.passes.size())) return fail("bad pass index", 1);

@@ -7,8 +7,11 @@
 
 namespace hq {
 
-int default_tile_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 12 : 11; }   // 32 KiB tiles
-int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 4; }  // 256-byte runs
+// Defaults come from the round-1 sweep on B200 (profiles/r01/sweep_b_after_kernel_opt.jsonl):
+// 64 KiB tiles (3 resident CTAs per SM) and 256 B / 512 B minimum runs.
+int default_tile_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 13 : 12; }
+int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 5; }
+int default_merge_max_k(int dtype) { return dtype == HQ_DTYPE_C64 ? 2 : 3; }
 
 namespace {
 
@@ -322,7 +325,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   }
 
   // ---- merge inside each pass, then serialise
-  const int merge_max_k = opts.merge_max_k < 0 ? 4 : std::min(opts.merge_max_k, HQ_SMALL_K);
+  const int merge_max_k = opts.merge_max_k < 0 ? default_merge_max_k(dtype) : std::min(opts.merge_max_k, HQ_SMALL_K);
   const int merge_pass_cost = opts.merge_pass_cost < 0 ? 12 : opts.merge_pass_cost;
   std::vector<std::vector<Cluster>> merged(drafts.size());
   size_t total_gates = 0;

@@ -33,7 +33,7 @@ struct PlanOptions {
   // to_matrix_gate, /root/reference/hybridq/circuit/utils.py:467, :419, default max 4 qubits).
   // Two gates of a pass are multiplied into one matrix when that does not raise the cost
   // cost(k) = 4 * 2^k + merge_pass_cost  (FMA per amplitude + one shared-memory round trip).
-  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (4)
+  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (2 c64 / 3 c128)
   int merge_pass_cost = -1; // -1 = default (12)
 };
 
@@ -57,6 +57,7 @@ struct Plan {
 
 int default_tile_bits(int dtype);
 int default_min_run_bits(int dtype);
+int default_merge_max_k(int dtype);
 
 // Build a plan.  Returns 0 on success; on failure returns non-zero and sets plan.error.
 int plan_build(Plan& plan, int dtype, unsigned n_qubits, const std::vector<GateIn>& gates,

@@ -310,6 +310,9 @@ class ShardedRunner:
                 total += e0.elapsed_time(e1)
         return total / reps
 
+    def extra_roofline(self, peak):
+        return {}
+
     def gather(self):
         """Full state on every rank (tests / small n only), canonical order required."""
         import torch

@@ -59,6 +59,7 @@ class Plan:
             raise _lib.HybridQB200Error(f"hq_plan_create failed: {_lib.last_error()}")
         self.n_gates = lib.hq_plan_num_gates(self._h)
         self.n_kernel_gates = lib.hq_plan_num_kernel_gates(self._h)
+        self.flops = lib.hq_plan_flops(self._h)
         self.n_passes = lib.hq_plan_num_passes(self._h)
 
     def __del__(self):

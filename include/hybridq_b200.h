@@ -119,14 +119,14 @@ int hq_scale_dev(void* state, int dtype, uint64_t n_amps, double factor, void* s
 typedef struct hq_plan hq_plan;
 
 typedef struct hq_plan_options {
-  int tile_bits;            /* log2 amplitudes per tile; 0 = default (12 c64 / 11 c128) */
+  int tile_bits;            /* log2 amplitudes per tile; 0 = default (13 c64 / 12 c128 = 64 KiB) */
   int min_run_bits;         /* smallest contiguous run the fuser may create; -1 = default */
   int fuse;                 /* 0 = one pass per gate */
   int max_gates_per_pass;   /* 0 = default */
   int lookahead;            /* 0 = default */
   int merge_max_k;          /* in-pass merging of gates into one matrix of at most this many qubits
                                (the reference's host-side `compress`, circuit/utils.py:467);
-                               0 = off, -1 = default (4) */
+                               0 = off, -1 = default (2 c64 / 3 c128) */
   int merge_pass_cost;      /* cost model: cost(k) = 4*2^k + merge_pass_cost; -1 = default (12) */
 } hq_plan_options;
 
@@ -143,6 +143,9 @@ int hq_plan_num_passes(const hq_plan* plan);
 int hq_plan_num_gates(const hq_plan* plan);
 /* number of matrices the kernels apply after in-pass merging (<= hq_plan_num_gates) */
 int hq_plan_num_kernel_gates(const hq_plan* plan);
+/* real floating-point operations one run of the plan performs: sum over kernel matrices of
+ * 8 * 2^k * 2^n (2^k complex multiply-adds per output amplitude) */
+double hq_plan_flops(const hq_plan* plan);
 /* per pass: {tile_bits, n_high, n_kernel_gates, has_perm, n_gate_ids, high_pos[0..n_high)}
  * -> out[0..5+n_high) */
 int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len);

@@ -46,7 +46,7 @@ if os.environ.get("HQ_GOLDEN_CHILD") != "1":
     env["LD_LIBRARY_PATH"] = f"{REFLIB}:" + env.get("LD_LIBRARY_PATH", "")
     env["PYTHONPATH"] = f"{REF}:{STUBS}:{ROOT}:" + env.get("PYTHONPATH", "")
     env["OMP_NUM_THREADS"] = "4"
-    os.execve(sys.executable, [sys.executable, "-W", "ignore", __file__], env)
+    os.execve(sys.executable, [sys.executable, "-W", "ignore", __file__] + sys.argv[1:], env)
 
 import numpy as np  # noqa: E402
 
@@ -268,11 +268,60 @@ def make_dm():
     np.savez_compressed(HERE / "dm.npz", **out)
 
 
+# ---------------------------------------------------------------- dm15_circuit.npz (config 5)
+def make_dm15():
+    """BASELINE config 5: 15-qubit depth-10 circuit + depolarizing noise, lowered by the reference's
+    dm front-end to a 30-"qubit" circuit.  Only the lowered gate list is stored (the 2^30 superket
+    has no CPU oracle); the GPU run checks trace / hermiticity and is timed by tools/run_configs.py."""
+    import hybridq.dm.circuit.simulation as dmsim
+    import hybridq.circuit.simulation as csim
+    from hybridq.gate import MatrixGate
+    from hybridq.circuit import Circuit, utils as cutils
+    from hybridq.noise.utils import add_depolarizing_noise
+
+    class _Captured(Exception):
+        pass
+
+    captured = {}
+
+    def spy(circuit, initial_state, **kw):
+        captured["circuit"] = list(circuit)
+        raise _Captured()
+
+    nq = 15
+    gates = matching_circuit(nq, depth=10, seed=1515)
+    circ = Circuit(MatrixGate(g.U, qubits=list(g.qubits)) for g in gates)
+    noisy = add_depolarizing_noise(circ, probs=(0.001, 0.01))
+    real = csim.simulate
+    csim.simulate = spy
+    try:
+        dmsim.simulate(noisy, initial_state="0", optimize="evolution", simplify=False, compress=0,
+                       complex_type="complex64", max_largest_intermediate=2 ** 30)
+    except _Captured:
+        pass
+    finally:
+        csim.simulate = real
+    lowered = list(cutils.flatten(Circuit(captured["circuit"])))
+    qubits = sorted({q for g in lowered for q in g.qubits})
+    assert len(qubits) == 2 * nq
+    out = {"n_super": np.int32(2 * nq), "ngates": np.int32(len(lowered))}
+    for j, g in enumerate(lowered):
+        out[f"g{j}_U"] = np.asarray(g.matrix()).astype(np.complex64)
+        out[f"g{j}_q"] = np.array([qubits.index(q) for q in g.qubits], dtype=np.int32)
+    np.savez_compressed(HERE / "dm15_circuit.npz", **out)
+    print(f"dm15_circuit.npz: {len(lowered)} lowered gates, k-hist = "
+          f"{np.bincount([len(g.qubits) for g in lowered])}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dm15":
+        make_dm15()
+        sys.exit(0)
     make_apply_u()
     make_swap()
     make_simulate()
     make_dot_transpose()
     make_dm()
+    make_dm15()
     for f in sorted(HERE.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size / 1e6:.2f} MB")
