@@ -26,13 +26,14 @@
 #define HQ_LDG(p) __ldg(p)
 #define HQ_UNROLL _Pragma("unroll")
 #define HQ_NOUNROLL _Pragma("unroll 1")
+#define HQ_ROWUNROLL _Pragma("unroll 2")
 #else
 #define HQ_DEV inline
 #define HQ_HD inline
 #define HQ_LDG(p) (*(p))
 #define HQ_UNROLL
 #define HQ_NOUNROLL
-#define HQ_NOUNROLL
+#define HQ_ROWUNROLL
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
@@ -160,7 +161,7 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc* __restrict__ g, const
         tile[sb ^ xo[i]] = make_float4(a0r, a0i, a1r, a1i);
       }
     } else {
-      HQ_NOUNROLL
+      HQ_ROWUNROLL
       for (int i = 0; i < DIM; ++i) {
         float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
         const float4* row = reinterpret_cast<const float4*>(U + i * DIM);
@@ -222,7 +223,7 @@ HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc* __restrict__ g, c
         tile[sb ^ xo[iu]] = make_float4(a0r, a0i, a1r, a1i);
       }
     } else {
-      HQ_NOUNROLL
+      HQ_ROWUNROLL
       for (int iu = 0; iu < UD; ++iu) {
         float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
         const float4* r0 = reinterpret_cast<const float4*>(U + (2 * iu) * DIM);
@@ -277,7 +278,7 @@ HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc* __restrict__ g, cons
         tile[sb ^ xo[i]] = make_double2(ar, ai);
       }
     } else {
-      HQ_NOUNROLL
+      HQ_ROWUNROLL
       for (int i = 0; i < DIM; ++i) {
         double ar = 0., ai = 0.;
         const double2* row = U + i * DIM;
