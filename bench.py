@@ -6,9 +6,10 @@
 
 A STEP is one evolution of the whole synthetic circuit (seeded depth-20
 random matching circuit of Haar 1-/2-qubit gates) over the state.  N = 1 runs BASELINE
-config[1]: n = 30, complex64 (8 GiB state).  N > 1 is weak scaling: n = 30 + log2 N, the
-top log2 N qubits sharded over the ranks, ~20 % of the gates touching a sharded qubit
-(config[3]'s structure at the same per-GPU shard as N = 1).
+config[1]: n = 30, complex64 (8 GiB state).  N > 1 is STRONG scaling by default: the same
+circuit and state, sharded over the ranks by the top log2 N qubits (which ~log2(N)/15 of the
+gates touch: 20 % at N = 8, config[3]'s crossing fraction).  `--scaling weak` instead grows the
+state with N (n = 30 + log2 N, config[3]'s circuit generator) at a fixed 8 GiB shard per GPU.
 
 value        gate-applies/s, state resident in HBM, timed with CUDA events (max over ranks)
 e2e          same metric through hybridq_b200.simulate(): pinned host state in, pinned host
@@ -41,13 +42,20 @@ CTYPE = "complex64"
 
 
 # ------------------------------------------------------------------------------------------
+SCALING = "strong"
+
+
 def workload(n_gpus: int):
     from hybridq_b200.circuits import matching_circuit, sharded_circuit, to_positions
     g = int(round(np.log2(n_gpus)))
-    n = N_BASE + g
-    if n_gpus == 1:
+    n = N_BASE + (g if SCALING == "weak" else 0)
+    if n_gpus == 1 or SCALING == "strong":
+        # strong scaling: the very same circuit and state at every N; at N > 1 the top g qubits are
+        # the rank, which in this circuit are touched by ~g/15 of the gates (20 % at N = 8)
         gates = matching_circuit(n, depth=DEPTH, seed=n)
         name = f"{n}-qubit depth-{DEPTH} random matching circuit (Haar 1-/2-qubit gates), {CTYPE}, seed {n}"
+        if n_gpus > 1:
+            name += f", state sharded over {n_gpus} GPUs by the top {g} qubits"
     else:
         gates = sharded_circuit(n, g, depth=DEPTH, frac_global=0.2, seed=n)
         name = (f"{n}-qubit depth-{DEPTH} random circuit, {CTYPE}, top {g} qubits sharded over {n_gpus} GPUs, "
@@ -193,7 +201,7 @@ def reference_arm(args):
               + ("" if n_cpu == n else f"; extrapolated x2^-{n - n_cpu} to n={n}"))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "gate-applies/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": SCALING, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "n_qubits": n, "depth": DEPTH},
             "cpu_baseline": {"value": rate, "unit": "gate-applies/s", "cores": cores, "kind": "reference",
                              "sample": sample, "tried": tried},
@@ -214,7 +222,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--n", type=int, default=0, help="override the number of qubits (diagnostics only)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     args = ap.parse_args()
+    global N_BASE, SCALING
+    SCALING = args.scaling
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -233,7 +244,6 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
-    global N_BASE
     if args.n:
         N_BASE = args.n
     n, gates, lowered, name = workload(world)
@@ -329,11 +339,12 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "gate-applies/s", "n_gpus": world, "steps": steps,
-                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": SCALING,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": name, "n_qubits": n, "depth": DEPTH, "gate_applies_per_step": n_gates,
                            "state_bytes_per_gpu": state_bytes // world,
-                           "l2": "state (8 GiB per GPU) is 65x larger than L2; no flush needed",
+                           "l2": f"state shard ({state_bytes // world >> 20} MiB per GPU) is larger than the 126 MB L2; "
+                                 "no flush needed",
                            "parallelism": runner.describe()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu}

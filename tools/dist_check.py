@@ -15,9 +15,9 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, nargs="+", default=[24, 28])
+ap.add_argument("--sizes", type=int, nargs="+", default=[24, 28])
 ap.add_argument("--ctypes", nargs="+", default=["complex64", "complex128"])
-ap.add_argument("--timing-n", type=int, default=0, help="also time a larger sharded run (no gather)")
+ap.add_argument("--timing-size", type=int, default=0, help="also time a larger sharded run (no gather)")
 args = ap.parse_args()
 
 import torch  # noqa: E402
@@ -36,7 +36,7 @@ out_path = ROOT / "gpurun_out" / "dist_check.jsonl"
 out_path.parent.mkdir(exist_ok=True)
 lines = []
 
-for n in args.n:
+for n in args.sizes:
     for ctype in args.ctypes:
         gates = sharded_circuit(n, g, depth=8, frac_global=0.25, seed=n)
         lowered, _ = to_positions(gates, qubits=list(range(n)))
@@ -62,8 +62,8 @@ for n in args.n:
         torch.cuda.empty_cache()
         dist.barrier()
 
-if args.timing_n:
-    n = args.timing_n
+if args.timing_size:
+    n = args.timing_size
     gates = sharded_circuit(n, g, depth=20, frac_global=0.2, seed=n)
     lowered, _ = to_positions(gates, qubits=list(range(n)))
     runner = ShardedRunner(n, lowered, "complex64", dist)
