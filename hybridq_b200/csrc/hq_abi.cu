@@ -216,6 +216,7 @@ hq::PlanOptions convert_opts(const hq_plan_options* o) {
     p.lookahead = o->lookahead;
     p.merge_max_k = o->merge_max_k;
     p.merge_pass_cost = o->merge_pass_cost;
+    p.fast_slots = o->fast_slots;
   }
   return p;
 }

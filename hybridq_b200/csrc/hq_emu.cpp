@@ -13,6 +13,20 @@
 
 namespace {
 
+void emu_fast_slot(float4* tile, int s, const HqGateDesc* g, const HqPassHeader& ph, int Tu, int tid) {
+  switch (s) {
+    case 0: hq::gate_fast_f32_k2<0>(tile, g, ph, Tu, tid); break;
+    case 1: hq::gate_fast_f32_k2<1>(tile, g, ph, Tu, tid); break;
+    case 2: hq::gate_fast_f32_k2<2>(tile, g, ph, Tu, tid); break;
+    case 3: hq::gate_fast_f32_k2<3>(tile, g, ph, Tu, tid); break;
+    case 4: hq::gate_fast_f32_k2<4>(tile, g, ph, Tu, tid); break;
+    case 5: hq::gate_fast_f32_k2<5>(tile, g, ph, Tu, tid); break;
+    case 6: hq::gate_fast_f32_k2<6>(tile, g, ph, Tu, tid); break;
+    default: hq::gate_fast_f32_k2<7>(tile, g, ph, Tu, tid); break;
+  }
+}
+void emu_fast_slot(double2*, int, const HqGateDesc*, const HqPassHeader&, int, int) {}
+
 template <typename T>
 void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned char* prog, const HqPassHeader& ph) {
   typedef typename hq::Traits<T>::Unit Unit;
@@ -35,7 +49,9 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
     }
     for (uint32_t gi = 0; gi < ph.n_gates; ++gi) {
       const HqGateDesc* g = gates + gi;
-      if (g->k <= HQ_SMALL_K) {
+      if (V == 1 && ph.max_k <= 2 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
+        for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
+      } else if (g->k <= HQ_SMALL_K) {
         const bool low = V == 1 && g->tpos[0] == 0;
         for (int tid = 0; tid < HQ_THREADS; ++tid)
           hq::gate_small_dispatch<4>(tile.data(), g, g->k, low, prog, g->mat_off, Tu, tid);
@@ -93,6 +109,7 @@ hq::PlanOptions make_opts(const int* o) {
     p.lookahead = o[4];
     p.merge_max_k = o[5];
     p.merge_pass_cost = o[6];
+    p.fast_slots = o[7];
   }
   return p;
 }
@@ -101,7 +118,8 @@ hq::PlanOptions make_opts(const int* o) {
 
 extern "C" {
 
-// opts = {tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead, merge_max_k, merge_pass_cost} or NULL.
+// opts = {tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead, merge_max_k, merge_pass_cost,
+// fast_slots} or NULL.
 // info_out (optional, >= 2 ints) receives {n_passes, n_gates}.
 int hq_emu_run_circuit(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
                        const double* U_flat, const int* opts, void* state_interleaved, int* info_out,

@@ -60,6 +60,45 @@ __device__ __forceinline__ void tile_fill(typename Traits<T>::Unit* tile,
   for (int i = 0; i < npt; ++i) cp_async16(&tile[swz_t ^ ph.iter_swz[i]], src + ph.iter_off[i]);
 }
 
+// One out-of-line copy of the generic register path per kernel (it is called from the unrolled
+// fast-slot sequence as well as from the tail loop).
+template <int MAXK, typename Unit>
+__device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g, uint32_t k, bool low,
+                                                const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
+  gate_small_dispatch<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
+}
+
+template <int S, int MAXK>
+__device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
+                                          const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
+  if (S < int(n_gates)) {
+    const HqGateDesc* g = gates + S;
+    if ((ph.fast_mask >> S) & 1u) {
+      gate_fast_f32_k2<S>(tile, g, ph, Tu, tid);
+    } else {
+      const bool low = __ldg(&g->tpos[0]) == 0;
+      gate_small_generic<MAXK>(tile, g, __ldg(&g->k), low, prog, __ldg(&g->mat_off), Tu, tid);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int MAXK>
+__device__ __forceinline__ void fast_slots(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
+                                           const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
+  fast_slot<0, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<1, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<2, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<3, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<4, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<5, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<6, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<7, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+}
+template <typename T, int MAXK>
+__device__ __forceinline__ void fast_slots(double2*, const HqGateDesc*, const HqPassHeader&, const unsigned char*,
+                                           uint32_t, int, int) {}
+
 template <typename T, int KCLASS, int NBUF>
 __global__ void __launch_bounds__(HQ_THREADS, (KCLASS <= 1 ? 3 : 2))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
@@ -111,13 +150,19 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     }
     __syncthreads();
 
-    for (uint32_t gi = 0; gi < n_gates; ++gi) {
+    uint32_t gi0 = 0;
+    if (V == 1 && KCLASS == 0 && ph.fast_mask) {
+      // unrolled slots: constant-bank matrices for the k = 2 gates, generic code for the others
+      gi0 = n_gates < HQ_FAST_SLOTS ? n_gates : HQ_FAST_SLOTS;
+      fast_slots<T, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+    }
+    for (uint32_t gi = gi0; gi < n_gates; ++gi) {
       const HqGateDesc* g = gates + gi;
       const uint32_t k = __ldg(&g->k);
       const uint32_t mat_off = __ldg(&g->mat_off);
       if (KCLASS < 3 || k <= HQ_SMALL_K) {
         const bool low = V == 1 && __ldg(&g->tpos[0]) == 0;
-        gate_small_dispatch<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
+        gate_small_generic<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
       } else {
         const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + mat_off);
         const int rounds = big_rounds(Tbits, int(k));

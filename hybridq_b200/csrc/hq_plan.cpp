@@ -391,6 +391,16 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         write_matrix<double>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
       mat_cursor += ((esz << (2 * c.k)) + 15) & ~size_t(15);
       ++gate_cursor;
+      {
+        const size_t slot = size_t(&cluster - &merged[di][0]);
+        if (dtype == HQ_DTYPE_C64 && opts.fast_slots != 0 && slot < HQ_FAST_SLOTS && c.k == 2 && gd.tpos[0] != 0) {
+          pi.header.fast_mask |= 1u << slot;
+          for (size_t e = 0; e < 16; ++e) {
+            pi.header.fast_u[slot][2 * e] = float(c.U[e].real());
+            pi.header.fast_u[slot][2 * e + 1] = float(c.U[e].imag());
+          }
+        }
+      }
       for (unsigned id : cluster.ids) pi.gate_ids.push_back(canon_id[id]);
       pi.header.max_k = std::max<uint32_t>(pi.header.max_k, c.k);
     }

@@ -65,7 +65,7 @@ class Emu:
         n = int(round(np.log2(psi.size)))
         ks, pos, U = self._pack(gates)
         st = np.ascontiguousarray(psi).copy()
-        o = (ctypes.c_int * 7)(*(tuple(opts) + (-1, -1))[:7]) if opts else None
+        o = (ctypes.c_int * 8)(*(tuple(opts) + (-1, -1, 1))[:8]) if opts else None
         info = (ctypes.c_int * 3)()
         err = ctypes.create_string_buffer(256)
         rc = self.lib.hq_emu_run_circuit(dt, n, len(gates), ks.ctypes.data_as(ctypes.c_void_p),
@@ -80,7 +80,7 @@ class Emu:
         n = int(round(np.log2(psi.size)))
         st = np.ascontiguousarray(psi).copy()
         p = np.ascontiguousarray(perm, dtype=np.uint32)
-        o = (ctypes.c_int * 7)(*(tuple(opts) + (-1, -1))[:7]) if opts else None
+        o = (ctypes.c_int * 8)(*(tuple(opts) + (-1, -1, 1))[:8]) if opts else None
         info = (ctypes.c_int * 3)()
         err = ctypes.create_string_buffer(256)
         rc = self.lib.hq_emu_bitperm(dt, n, p.ctypes.data_as(ctypes.c_void_p), o,
@@ -93,7 +93,7 @@ class Emu:
         """Planner only: returns list of passes {tile_bits, n_high, n_gates, has_perm, high_pos, gate_ids}."""
         ks = np.array([len(p) for p in gates_pos], dtype=np.uint32)
         pos = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint32) for p in gates_pos]))
-        o = (ctypes.c_int * 7)(*(tuple(opts) + (-1, -1))[:7]) if opts else None
+        o = (ctypes.c_int * 8)(*(tuple(opts) + (-1, -1, 1))[:8]) if opts else None
         out = np.zeros(64 * (len(gates_pos) + 4), dtype=np.uint32)
         w = self.lib.hq_emu_plan_dump(dtype, n, len(gates_pos), ks.ctypes.data_as(ctypes.c_void_p),
                                       pos.ctypes.data_as(ctypes.c_void_p), o,

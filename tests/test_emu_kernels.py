@@ -31,7 +31,8 @@ def test_random_circuits_vs_oracle(emu, oracle, c_oracle, ctype, n):
         gates = [_rand_gate(rng, n, int(rng.integers(1, min(n, 7) + 1))) for _ in range(int(rng.integers(1, 14)))]
         ref = oracle.evolve_oracle(psi, [(u.astype(ctype), p) for u, p in gates], c_oracle)
         for opts in (None, (8, 2, 1, 0, 0), (8, 3, 0, 0, 0), (9, 1, 1, 4, 0), (13, 5, 1, 0, 0),
-                     (9, 2, 1, 0, 0, 0, -1), (10, 2, 1, 0, 0, 2, 0), (12, 3, 1, 0, 0, 3, 30)):
+                     (9, 2, 1, 0, 0, 0, -1), (10, 2, 1, 0, 0, 2, 0), (12, 3, 1, 0, 0, 3, 30),
+                     (11, 2, 1, 0, 0, 2, -1, 0)):
             out, n_pass, n_gates = emu.run(psi, gates, opts)
             assert n_gates == len(gates)
             assert np.abs(out - ref).max() < tol, (ctype, n, trial, opts)

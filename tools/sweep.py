@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--n128", type=int, default=29)
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "sweep.jsonl"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
     args = ap.parse_args()
     import torch
     import hybridq_b200 as hb
@@ -68,7 +69,7 @@ def main():
             5: [[2, 8, 14, 20, 26]],
             6: [[1, 6, 11, 16, 21, 26]],
         }
-        ks = [1, 2] if args.quick else [1, 2, 3, 4, 5, 6]
+        ks = [] if args.no_single else ([1, 2] if args.quick else [1, 2, 3, 4, 5, 6])
         for k in ks:
             U = haar_unitary(2 ** k, rng)
             for pos in placements[k]:
@@ -101,21 +102,23 @@ def main():
         tiles = [12, 13] if ctype == "complex64" else [11, 12]
         for T in tiles:
             for min_run in (4, 5):
-                for merge in (0, 2, 3, 4):
-                    for nbuf in (1, 2):
-                        hb.lib.hq_set_tuning(nbuf, 0, -1)
-                        try:
-                            plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(T, min_run, 1, 0, 0, merge, -1))
-                            ms = timed(lambda: plan.run(st), warm=1, reps=2)
-                        except Exception as e:
+                for merge in (2, 3):
+                    for fast in ((1, 0) if ctype == "complex64" else (1,)):
+                        for nbuf in (0, 1):
+                            hb.lib.hq_set_tuning(nbuf, 0, -1)
+                            try:
+                                plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(T, min_run, 1, 0, 0, merge, -1, fast))
+                                ms = timed(lambda: plan.run(st), warm=1, reps=2)
+                            except Exception as e:
+                                emit({"what": "circuit", "ctype": ctype, "n": n, "T": T, "min_run": min_run,
+                                      "nbuf": nbuf, "merge": merge, "fast": fast, "error": str(e)})
+                                continue
                             emit({"what": "circuit", "ctype": ctype, "n": n, "T": T, "min_run": min_run, "nbuf": nbuf,
-                                  "merge": merge, "error": str(e)})
-                            continue
-                        emit({"what": "circuit", "ctype": ctype, "n": n, "T": T, "min_run": min_run, "nbuf": nbuf,
-                              "merge": merge, "gates": plan.n_gates, "kernel_gates": plan.n_kernel_gates,
-                              "passes": plan.n_passes, "ms": ms, "gate_applies_per_s": plan.n_gates / ms * 1e3,
-                              "ms_per_pass": ms / plan.n_passes,
-                              "GBps_per_pass": bytes_pass * plan.n_passes / ms / 1e6})
+                                  "merge": merge, "fast": fast, "gates": plan.n_gates,
+                                  "kernel_gates": plan.n_kernel_gates, "passes": plan.n_passes, "ms": ms,
+                                  "gate_applies_per_s": plan.n_gates / ms * 1e3, "ms_per_pass": ms / plan.n_passes,
+                                  "tflops": plan.flops / ms / 1e9,
+                                  "GBps_per_pass": bytes_pass * plan.n_passes / ms / 1e6})
         hb.lib.hq_set_tuning(0, 0, 1)
         # unfused reference point
         plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(0, -1, 0, 0, 0, 0, -1))
