@@ -2,6 +2,12 @@ import os
 import sys
 from pathlib import Path
 
+# The C oracle and numpy/scipy use OpenMP / BLAS thread pools; a handful of threads is plenty for
+# the test sizes and keeps many-core boxes from oversubscribing next to torch's own pools.
+os.environ.setdefault("OMP_NUM_THREADS", "4")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "4")
+os.environ.setdefault("MKL_NUM_THREADS", "4")
+
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent

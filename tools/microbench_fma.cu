@@ -10,7 +10,7 @@
 
 #include <cstdio>
 
-struct Consts { float c[64]; };
+struct Consts { float c[64]; double d[64]; };
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_fma(float* out, int iters, float a0, float b0, const __grid_constant__ Consts cs) {
@@ -80,6 +80,23 @@ __global__ void __launch_bounds__(256) k_dfma(float* out, int iters, double a0, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = float(s);
 }
 
+__global__ void __launch_bounds__(256) k_dfma_const(float* out, int iters, double b0, const __grid_constant__ Consts cs) {
+  double acc[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = threadIdx.x * 1e-3 + i; b[i] = b0 + i * 1e-4; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fma_rn(acc[i], cs.d[r * 8 + i], b[i]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = float(s);
+}
+
 template <typename F>
 static double time_ms(F launch) {
   cudaEvent_t e0, e1;
@@ -103,7 +120,7 @@ int main() {
   float* out;
   cudaMalloc(&out, size_t(blocks) * threads * sizeof(float));
   Consts cs;
-  for (int i = 0; i < 64; ++i) cs.c[i] = 1.0f - 1e-6f * i;
+  for (int i = 0; i < 64; ++i) { cs.c[i] = 1.0f - 1e-6f * i; cs.d[i] = 1.0 - 1e-9 * i; }
   const double fmas = double(blocks) * threads * double(iters) * 64.0;
   double ms;
   ms = time_ms([&] { k_fma<0><<<blocks, threads>>>(out, iters, 0.999f, 1e-3f, cs); });
@@ -116,6 +133,8 @@ int main() {
   printf("{\"what\": \"FFMA2 (fma.rn.f32x2)\", \"ms\": %.3f, \"TFMA_per_s\": %.2f, \"TFLOPs\": %.2f}\n", ms, 2 * fmas / ms / 1e9, 4 * fmas / ms / 1e9);
   ms = time_ms([&] { k_dfma<<<blocks, threads>>>(out, iters / 4, 0.999, 1e-3); });
   printf("{\"what\": \"DFMA\", \"ms\": %.3f, \"TFMA_per_s\": %.2f, \"TFLOPs\": %.2f}\n", ms, fmas / 4 / ms / 1e9, 2 * fmas / 4 / ms / 1e9);
+  ms = time_ms([&] { k_dfma_const<<<blocks, threads>>>(out, iters / 4, 1e-3, cs); });
+  printf("{\"what\": \"DFMA const-bank operand\", \"ms\": %.3f, \"TFMA_per_s\": %.2f, \"TFLOPs\": %.2f}\n", ms, fmas / 4 / ms / 1e9, 2 * fmas / 4 / ms / 1e9);
   cudaFree(out);
   return 0;
 }
