@@ -217,6 +217,17 @@ class CudaEngine:
     def init_random(self, st, seed, index_offset):
         st.init_random(seed=seed, index_offset=index_offset, scale=1.0)
 
+    def init_product(self, st, spec_local, factor):
+        st.init_product(spec_local)
+        if factor != 1.0:
+            st.scale(factor)
+
+    def upload(self, st, host):
+        st.upload(host)
+
+    def download(self, st, out=None):
+        return st.download(out)
+
     def norm2(self, st):
         return st.norm2()
 
@@ -262,6 +273,26 @@ class ShardedRunner:
         n2 = self.engine.norm2(self.a)
         tot = self._allreduce_sum(n2)
         self.engine.scale(self.a, 1.0 / math.sqrt(tot))
+
+    def init_product(self, spec: str):
+        """Product state from a string of n characters 0,1,+,- (spec[0] = most significant bit):
+        the rank bits select a scalar factor, the local bits a local product state."""
+        if len(spec) == 1:
+            spec = spec * self.n
+        if len(spec) != self.n:
+            raise ValueError("Wrong number of qubits for initial/final state.")
+        r = 2 ** -0.5
+        factor = 1.0
+        for j in range(self.g):                      # spec[j] <-> index bit n-1-j = rank bit g-1-j
+            bit = (self.rank >> (self.g - 1 - j)) & 1
+            factor *= {"0": (1, 0), "1": (0, 1), "+": (r, r), "-": (r, -r)}[spec[j]][bit]
+        self.engine.init_product(self.a, spec[self.g:], factor)
+
+    def load_shard(self, host_shard):
+        self.engine.upload(self.a, host_shard)
+
+    def download_shard(self, out=None):
+        return self.engine.download(self.a, out)
 
     def _allreduce_sum(self, v: float) -> float:
         import torch

@@ -119,6 +119,8 @@ def simulate(circuit,
     kwargs.setdefault("plan_options", None)
     kwargs.setdefault("device", None)
     kwargs.setdefault("out", None)           # optional (e.g. pinned) complex array receiving the result
+    kwargs.setdefault("shard", "auto")       # True / False / 'auto': shard the state over the ranks of an
+                                             # initialised torch.distributed process group (one GPU per rank)
 
     hq = _try_hybridq()
     is_ref_circuit = False
@@ -220,6 +222,10 @@ def simulate(circuit,
         segments.append(("gates", cur))
     t_pre = time.perf_counter() - t_pre
 
+    dist = _dist_if_sharded(kwargs["shard"])
+    if dist is not None:
+        return _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwargs, t_pre)
+
     t_plan = time.perf_counter()
     opts: PlanOptions | None = kwargs["plan_options"]
     plans = [(kind, Plan(payload, n_qubits, complex_type, opts) if kind == "gates" else payload)
@@ -258,6 +264,63 @@ def simulate(circuit,
         info["download (s)"] = time.perf_counter() - t_down
     else:
         psi = state
+    return (psi, info) if kwargs["return_info"] else psi
+
+
+def _dist_if_sharded(shard):
+    """torch.distributed module if the state is to be sharded over its ranks, else None."""
+    if shard is False:
+        return None
+    try:
+        import torch.distributed as dist
+    except Exception:
+        dist = None
+    ok = dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if shard is True and not ok:
+        raise RuntimeError("shard=True needs an initialised torch.distributed process group with > 1 rank")
+    return dist if ok else None
+
+
+def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwargs, t_pre):
+    """Multi-GPU evolution (hybridq_b200.dist): every rank calls simulate() with the same circuit; an
+    array initial state is the FULL state on every rank (each uploads its own slice) or, if it has
+    2^(n - log2 p) amplitudes, this rank's shard.  Returns this rank's shard of the final state
+    (amplitudes [rank * 2^(n-g), (rank+1) * 2^(n-g)) in canonical order).  The reference has no
+    counterpart (simulation.py:379-380)."""
+    from .dist import ShardedRunner
+    if any(kind != "gates" for kind, _ in segments):
+        raise NotImplementedError("FunctionalGates are not supported on a sharded state")
+    lowered = [gp for _, payload in segments for gp in payload]
+    t_plan = time.perf_counter()
+    runner = ShardedRunner(n_qubits, lowered, complex_type, dist, plan_options=kwargs["plan_options"])
+    t_plan = time.perf_counter() - t_plan
+    nl = runner.n_local
+    t_up = time.perf_counter()
+    if isinstance(initial_state, str):
+        runner.init_product(initial_state)
+    else:
+        flat = np.asarray(initial_state).reshape(-1)
+        if flat.size == 2 ** n_qubits:
+            flat = flat[runner.rank * 2 ** nl:(runner.rank + 1) * 2 ** nl]
+        elif flat.size != 2 ** nl:
+            raise ValueError("Wrong number of qubits for initial/final state.")
+        runner.load_shard(np.ascontiguousarray(flat, dtype=complex_type))
+    runner.engine.sync()
+    t_up = time.perf_counter() - t_up
+    dist.barrier()
+    t0 = time.perf_counter()
+    runner.step()
+    runner.engine.sync()
+    dist.barrier()
+    runtime = time.perf_counter() - t0
+    info = {"runtime (s)": runtime, "pre-pass (s)": t_pre, "plan (s)": t_plan, "upload (s)": t_up,
+            "n_gate_applies": runner.n_gates, "n_passes": runner.local_passes, "n_qubits": n_qubits,
+            "shard": (runner.rank, runner.world), "n_local_qubits": nl, "exchange stats": runner.stats}
+    if kwargs["return_numpy_array"]:
+        out = kwargs["out"]
+        psi = runner.download_shard(out.reshape(-1) if out is not None else None).reshape((2,) * nl)
+    else:
+        psi = runner.a
     return (psi, info) if kwargs["return_info"] else psi
 
 

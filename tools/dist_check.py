@@ -62,6 +62,22 @@ for n in args.sizes:
         torch.cuda.empty_cache()
         dist.barrier()
 
+# the public entry point on a sharded state: every rank calls simulate() with the same arguments
+from hybridq_b200.circuits import matching_circuit  # noqa: E402
+n = 22
+gates = matching_circuit(n, depth=6, seed=5)
+shard, info = hb.simulate(gates, initial_state="+-01" * 5 + "0+", complex_type="complex128", return_info=True)
+full_parts = [torch.empty(shard.size, dtype=torch.complex128, device="cuda") for _ in range(world)]
+dist.all_gather(full_parts, torch.from_numpy(shard.reshape(-1).copy()).cuda())
+if rank == 0:
+    ref = hb.simulate(gates, initial_state="+-01" * 5 + "0+", complex_type="complex128", shard=False).reshape(-1)
+    err = float(np.abs(torch.cat(full_parts).cpu().numpy() - ref).max())
+    rec = {"simulate_sharded_n": n, "world": world, "max_abs_err_vs_1gpu": err, "ok": bool(err <= 1e-12),
+           "info": {k: v for k, v in info.items() if k in ("n_passes", "n_gate_applies", "shard", "exchange stats")}}
+    print(json.dumps(rec), flush=True)
+    lines.append(rec)
+dist.barrier()
+
 if args.timing_size:
     n = args.timing_size
     gates = sharded_circuit(n, g, depth=20, frac_global=0.2, seed=n)
