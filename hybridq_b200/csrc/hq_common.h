@@ -29,14 +29,15 @@
 
 #define HQ_GATE_SMALL 0
 #define HQ_GATE_BIG 1
+#define HQ_GATE_ROWPAIR 2     // complex128 k = 2, 3: row-pair scheme (see HqGateDesc::tbl_rthread)
 
 #define HQ_MAX_PER_THREAD 16   // units per thread per tile = 2^(unit bits - 8) <= 16
 #define HQ_MAX_PASS_GATES 24   // kernel matrices per pass after merging
 #define HQ_FAST_SLOTS 8        // unrolled constant-bank gate slots per pass (complex64, k = 2)
 
-struct HqGateDesc {        // 624 bytes, lives in the device program buffer (read through L1)
+struct HqGateDesc {        // 1168 bytes, lives in the device program buffer (read through L1)
   uint32_t k;              // number of target bits
-  uint32_t kind;           // HQ_GATE_SMALL / HQ_GATE_BIG
+  uint32_t kind;           // HQ_GATE_SMALL / HQ_GATE_BIG / HQ_GATE_ROWPAIR
   uint32_t mat_off;        // byte offset of the matrix from the program base
                            //   small: row-major 2^k x 2^k, interleaved (re, im)
                            //   big  : column-major (transposed), interleaved
@@ -51,6 +52,12 @@ struct HqGateDesc {        // 624 bytes, lives in the device program buffer (rea
   uint16_t tbl_thread[HQ_THREADS];
   uint16_t tbl_iter[16];
   uint16_t tbl_x[16];
+  // complex128 "row-pair" scheme (k = 2, 3): thread tid = (group slot gs, row pair rp) with
+  // rp = tid & (2^(k-1) - 1), gs = tid >> (k-1); the units of its group are
+  //   slot(gs, it, m) = tbl_rthread[gs] ^ tbl_riter[it] ^ tbl_x[m]
+  // and it produces rows 2rp, 2rp+1 of the group with those two matrix rows held in registers.
+  uint16_t tbl_rthread[HQ_THREADS];
+  uint16_t tbl_riter[16];
 };
 
 struct HqPassHeader {      // passed to the kernel by value (constant bank)
@@ -81,5 +88,5 @@ struct HqPassHeader {      // passed to the kernel by value (constant bank)
   float fast_u[HQ_FAST_SLOTS][32];
 };
 
-static_assert(sizeof(HqGateDesc) == 624, "HqGateDesc layout");
+static_assert(sizeof(HqGateDesc) == 624 + 512 + 32, "HqGateDesc layout");
 static_assert(sizeof(HqPassHeader) == 256 + 8 + 4 * 32 * HQ_FAST_SLOTS, "HqPassHeader layout");

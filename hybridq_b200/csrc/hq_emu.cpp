@@ -27,6 +27,35 @@ void emu_fast_slot(float4* tile, int s, const HqGateDesc* g, const HqPassHeader&
 }
 void emu_fast_slot(double2*, int, const HqGateDesc*, const HqPassHeader&, int, int) {}
 
+template <int KK>
+void emu_rowpair_k(double2* tile, const HqGateDesc* g, const double2* U, int Tu) {
+  std::vector<hq::RowPairRegs<KK>> regs(HQ_THREADS);
+  for (int tid = 0; tid < HQ_THREADS; ++tid) {
+    hq::rowpair_load_rows<KK>(regs[size_t(tid)], U, tid);
+    hq::rowpair_load_offsets<KK>(regs[size_t(tid)], g);
+  }
+  const uint32_t niter = hq::rowpair_iters(Tu, KK);
+  for (uint32_t it = 0; it < niter; ++it) {
+    std::vector<double2> o0(HQ_THREADS), o1(HQ_THREADS);
+    std::vector<uint32_t> s0(HQ_THREADS), s1(HQ_THREADS);
+    std::vector<char> ok(HQ_THREADS);
+    for (int tid = 0; tid < HQ_THREADS; ++tid)
+      ok[size_t(tid)] = hq::rowpair_compute<KK>(tile, g, regs[size_t(tid)], Tu, tid, it, o0[size_t(tid)],
+                                                o1[size_t(tid)], s0[size_t(tid)], s1[size_t(tid)]);
+    for (int tid = 0; tid < HQ_THREADS; ++tid)
+      if (ok[size_t(tid)]) {
+        tile[s0[size_t(tid)]] = o0[size_t(tid)];
+        tile[s1[size_t(tid)]] = o1[size_t(tid)];
+      }
+  }
+}
+void emu_rowpair(double2* tile, const HqGateDesc* g, const unsigned char* prog, int Tu) {
+  const double2* U = reinterpret_cast<const double2*>(prog + g->mat_off);
+  if (g->k == 2) emu_rowpair_k<2>(tile, g, U, Tu);
+  else emu_rowpair_k<3>(tile, g, U, Tu);
+}
+void emu_rowpair(float4*, const HqGateDesc*, const unsigned char*, int) {}
+
 template <typename T>
 void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned char* prog, const HqPassHeader& ph) {
   typedef typename hq::Traits<T>::Unit Unit;
@@ -51,6 +80,8 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
       const HqGateDesc* g = gates + gi;
       if (V == 1 && ph.max_k <= 2 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
         for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
+      } else if (V == 0 && g->kind == HQ_GATE_ROWPAIR) {
+        emu_rowpair(tile.data(), g, prog, Tu);
       } else if (g->k <= HQ_SMALL_K) {
         const bool low = V == 1 && g->tpos[0] == 0;
         for (int tid = 0; tid < HQ_THREADS; ++tid)

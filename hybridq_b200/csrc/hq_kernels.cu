@@ -68,6 +68,17 @@ __device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g,
   gate_small_dispatch<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
 }
 
+template <int MAXK>
+__device__ __forceinline__ void rowpair_dispatch(double2* tile, const HqGateDesc* g, uint32_t k,
+                                                 const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
+  const double2* U = reinterpret_cast<const double2*>(prog + mat_off);
+  if (k == 2) gate_rowpair_f64<2>(tile, g, U, Tu, tid);
+  else if (MAXK >= 3) gate_rowpair_f64<3>(tile, g, U, Tu, tid);
+}
+template <int MAXK>
+__device__ __forceinline__ void rowpair_dispatch(float4*, const HqGateDesc*, uint32_t, const unsigned char*, uint32_t,
+                                                 int, int) {}
+
 template <int S, int MAXK>
 __device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
                                           const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
@@ -100,7 +111,7 @@ __device__ __forceinline__ void fast_slots(double2*, const HqGateDesc*, const Hq
                                            uint32_t, int, int) {}
 
 template <typename T, int KCLASS, int NBUF>
-__global__ void __launch_bounds__(HQ_THREADS, (KCLASS <= 1 ? 3 : 2))
+__global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 || (KCLASS == 1 && Traits<T>::V == 1)) ? 3 : 2))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
                const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles) {
   typedef typename Traits<T>::Unit Unit;
@@ -160,7 +171,9 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
       const HqGateDesc* g = gates + gi;
       const uint32_t k = __ldg(&g->k);
       const uint32_t mat_off = __ldg(&g->mat_off);
-      if (KCLASS < 3 || k <= HQ_SMALL_K) {
+      if (V == 0 && __ldg(&g->kind) == HQ_GATE_ROWPAIR) {
+        rowpair_dispatch<MAXK>(tile, g, k, prog, mat_off, Tu, tid);
+      } else if (KCLASS < 3 || k <= HQ_SMALL_K) {
         const bool low = V == 1 && __ldg(&g->tpos[0]) == 0;
         gate_small_generic<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
       } else {

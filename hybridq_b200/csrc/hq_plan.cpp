@@ -111,6 +111,21 @@ void make_lane_tables(HqGateDesc& gd, int Tu, int V) {
     gd.tbl_x[m] = m < (1 << KK) ? uint16_t(swz(uint32_t(deposit(uint32_t(m), upos, KK)))) : uint16_t(0);
 }
 
+// Lane tables of the complex128 row-pair scheme (see HqGateDesc).
+void make_rowpair_tables(HqGateDesc& gd, int Tu) {
+  const int KK = int(gd.k);
+  if (KK < 2 || KK > 3) return;
+  const int lrp = KK - 1;
+  const int nq = Tu - KK;
+  const int gbits = HQ_THREADS_LOG2 - lrp;                 // group slots per iteration = 2^gbits
+  const int tb = nq < gbits ? nq : gbits;
+  for (int gs = 0; gs < HQ_THREADS; ++gs)
+    gd.tbl_rthread[gs] = uint16_t(swz(scatter_bits(uint32_t(gs) & ((1u << tb) - 1u), gd.q, 0, tb)));
+  const int niter = 1 << (nq - tb);
+  for (int it = 0; it < 16; ++it)
+    gd.tbl_riter[it] = it < niter ? uint16_t(swz(scatter_bits(uint32_t(it), gd.q, tb, nq))) : uint16_t(0);
+}
+
 int local_bit(const HqPassHeader& ph, unsigned global_bit) {
   const int L = int(ph.tile_bits) - int(ph.n_high);
   if (int(global_bit) < L) return int(global_bit);
@@ -384,6 +399,10 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       gd.n_free = uint32_t(free_bits.size());
       for (size_t i = 0; i < free_bits.size() && i < 16; ++i) gd.q[i] = uint8_t(free_bits[i]);
       if (gd.kind == HQ_GATE_SMALL) make_lane_tables(gd, Tu, V);
+      if (gd.kind == HQ_GATE_SMALL && dtype == HQ_DTYPE_C128 && opts.fast_slots != 0 && (gd.k == 2 || gd.k == 3)) {
+        make_rowpair_tables(gd, Tu);
+        gd.kind = HQ_GATE_ROWPAIR;
+      }
       memcpy(plan.program.data() + gate_cursor * sizeof(HqGateDesc), &gd, sizeof(gd));
       if (dtype == HQ_DTYPE_C64)
         write_matrix<float>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);

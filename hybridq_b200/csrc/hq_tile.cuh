@@ -327,6 +327,88 @@ HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc* __restrict__ g, cons
   }
 }
 
+// complex128, row-pair scheme for K = 2, 3: a group's 2^K rows are produced by 2^(K-1) adjacent
+// lanes, each holding two matrix rows in registers for the whole gate, so one 16-byte shared
+// load feeds 8 DFMAs (the plain scheme above feeds 4 and is bound by the matrix loads).
+// The lanes of a group sit in one warp: a __syncwarp() between the loads and the stores keeps
+// the update in place.  `sync_warp` is a no-op in the CPU emulation (lanes run in sequence there,
+// so the emulation splits the function in two phases instead).
+template <int KK>
+struct RowPairRegs {
+  double2 u0[1 << KK], u1[1 << KK];
+  uint32_t xo[1 << KK];
+};
+
+template <int KK>
+HQ_DEV void rowpair_load_rows(RowPairRegs<KK>& r, const double2* __restrict__ U, int tid) {
+  const int DIM = 1 << KK;
+  const int rp = tid & ((DIM >> 1) - 1);
+  HQ_UNROLL
+  for (int j = 0; j < DIM; ++j) {
+    r.u0[j] = HQ_LDG(&U[(2 * rp) * DIM + j]);
+    r.u1[j] = HQ_LDG(&U[(2 * rp + 1) * DIM + j]);
+  }
+}
+template <int KK>
+HQ_DEV void rowpair_load_offsets(RowPairRegs<KK>& r, const HqGateDesc* __restrict__ g) {
+  HQ_UNROLL
+  for (int j = 0; j < (1 << KK); ++j) r.xo[j] = HQ_LDG(&g->tbl_x[j]);
+}
+
+// phase A of one iteration: gather the group's inputs and compute the two output rows
+template <int KK>
+HQ_DEV bool rowpair_compute(const double2* tile, const HqGateDesc* __restrict__ g, const RowPairRegs<KK>& r,
+                            int Tu, int tid, uint32_t it, double2& o0, double2& o1, uint32_t& s0, uint32_t& s1) {
+  const int DIM = 1 << KK;
+  const int lrp = KK - 1;
+  const int nq = Tu - KK;
+  const uint32_t gs = uint32_t(tid) >> lrp;
+  const int gbits = HQ_THREADS_LOG2 - lrp;
+  if (nq < gbits && gs >= (1u << nq)) return false;
+  const uint32_t rp = uint32_t(tid) & ((DIM >> 1) - 1);
+  const uint32_t sb = uint32_t(HQ_LDG(&g->tbl_rthread[gs])) ^ uint32_t(HQ_LDG(&g->tbl_riter[it]));
+  double a0r = 0., a0i = 0., a1r = 0., a1i = 0.;
+  HQ_UNROLL
+  for (int j = 0; j < DIM; ++j) {
+    const double2 x = tile[sb ^ r.xo[j]];
+    cmac(a0r, a0i, r.u0[j].x, r.u0[j].y, x.x, x.y);
+    cmac(a1r, a1i, r.u1[j].x, r.u1[j].y, x.x, x.y);
+  }
+  o0 = make_double2(a0r, a0i);
+  o1 = make_double2(a1r, a1i);
+  s0 = sb ^ uint32_t(HQ_LDG(&g->tbl_x[2 * rp]));
+  s1 = sb ^ uint32_t(HQ_LDG(&g->tbl_x[2 * rp + 1]));
+  return true;
+}
+
+HQ_DEV uint32_t rowpair_iters(int Tu, int KK) {
+  const int nq = Tu - KK;
+  const int gbits = HQ_THREADS_LOG2 - (KK - 1);
+  return nq > gbits ? (1u << (nq - gbits)) : 1u;
+}
+
+#ifdef __CUDACC__
+template <int KK>
+__device__ __forceinline__ void gate_rowpair_f64(double2* tile, const HqGateDesc* __restrict__ g,
+                                                 const double2* __restrict__ U, int Tu, int tid) {
+  RowPairRegs<KK> r;
+  rowpair_load_rows<KK>(r, U, tid);
+  rowpair_load_offsets<KK>(r, g);
+  const uint32_t niter = rowpair_iters(Tu, KK);
+  HQ_NOUNROLL
+  for (uint32_t it = 0; it < niter; ++it) {
+    double2 o0, o1;
+    uint32_t s0 = 0, s1 = 0;
+    const bool ok = rowpair_compute<KK>(tile, g, r, Tu, tid, it, o0, o1, s0, s1);
+    __syncwarp();              // every lane of the group has read its inputs
+    if (ok) {
+      tile[s0] = o0;
+      tile[s1] = o1;
+    }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // two-phase path for k >= 5 (amplitude granularity, any precision).  A round handles
 // HQ_THREADS * HQ_BIG_ROWS / 2^k whole groups: in phase A every thread accumulates

@@ -101,9 +101,9 @@ def main():
         lowered, _ = to_positions(gates, qubits=list(range(n)))
         tiles = [12, 13] if ctype == "complex64" else [11, 12]
         for T in tiles:
-            for min_run in (4, 5):
+            for min_run in (5,):
                 for merge in (2, 3):
-                    for fast in ((1, 0) if ctype == "complex64" else (1,)):
+                    for fast in (1, 0):
                         for nbuf in (0, 1):
                             hb.lib.hq_set_tuning(nbuf, 0, -1)
                             try:
