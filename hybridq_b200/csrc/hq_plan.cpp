@@ -11,7 +11,7 @@ namespace hq {
 // 64 KiB tiles (3 resident CTAs per SM) and 256 B / 512 B minimum runs.
 int default_tile_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 13 : 12; }
 int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 5; }
-int default_merge_max_k(int dtype) { return dtype == HQ_DTYPE_C64 ? 2 : 3; }
+int default_merge_max_k(int) { return 2; }
 
 namespace {
 

@@ -33,7 +33,7 @@ struct PlanOptions {
   // to_matrix_gate, /root/reference/hybridq/circuit/utils.py:467, :419, default max 4 qubits).
   // Two gates of a pass are multiplied into one matrix when that does not raise the cost
   // cost(k) = 4 * 2^k + merge_pass_cost  (FMA per amplitude + one shared-memory round trip).
-  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (2 c64 / 3 c128)
+  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (2)
   int merge_pass_cost = -1; // -1 = default (12)
   int fast_slots = 1;       // 0 = never use the constant-bank fast slots (measurements)
 };

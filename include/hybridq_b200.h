@@ -126,7 +126,7 @@ typedef struct hq_plan_options {
   int lookahead;            /* 0 = default */
   int merge_max_k;          /* in-pass merging of gates into one matrix of at most this many qubits
                                (the reference's host-side `compress`, circuit/utils.py:467);
-                               0 = off, -1 = default (2 c64 / 3 c128) */
+                               0 = off, -1 = default (2) */
   int merge_pass_cost;      /* cost model: cost(k) = 4*2^k + merge_pass_cost; -1 = default (12) */
   int fast_slots;           /* complex64: pass the first 8 k=2 matrices of a pass as kernel parameters
                                (constant-bank FFMA operands); 0 = off, anything else = on (default) */
