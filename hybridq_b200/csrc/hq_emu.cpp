@@ -14,17 +14,15 @@
 namespace {
 
 void emu_fast_slot(float4* tile, int s, const HqGateDesc* g, const HqPassHeader& ph, int Tu, int tid) {
-  hq::SlotTables t;
-  hq::slot_tables_load(t, g, tid);
   switch (s) {
-    case 0: hq::gate_fast_f32_k2<0>(tile, g, ph, t, Tu, tid); break;
-    case 1: hq::gate_fast_f32_k2<1>(tile, g, ph, t, Tu, tid); break;
-    case 2: hq::gate_fast_f32_k2<2>(tile, g, ph, t, Tu, tid); break;
-    case 3: hq::gate_fast_f32_k2<3>(tile, g, ph, t, Tu, tid); break;
-    case 4: hq::gate_fast_f32_k2<4>(tile, g, ph, t, Tu, tid); break;
-    case 5: hq::gate_fast_f32_k2<5>(tile, g, ph, t, Tu, tid); break;
-    case 6: hq::gate_fast_f32_k2<6>(tile, g, ph, t, Tu, tid); break;
-    default: hq::gate_fast_f32_k2<7>(tile, g, ph, t, Tu, tid); break;
+    case 0: hq::gate_fast_f32_k2<0>(tile, g, ph, Tu, tid); break;
+    case 1: hq::gate_fast_f32_k2<1>(tile, g, ph, Tu, tid); break;
+    case 2: hq::gate_fast_f32_k2<2>(tile, g, ph, Tu, tid); break;
+    case 3: hq::gate_fast_f32_k2<3>(tile, g, ph, Tu, tid); break;
+    case 4: hq::gate_fast_f32_k2<4>(tile, g, ph, Tu, tid); break;
+    case 5: hq::gate_fast_f32_k2<5>(tile, g, ph, Tu, tid); break;
+    case 6: hq::gate_fast_f32_k2<6>(tile, g, ph, Tu, tid); break;
+    default: hq::gate_fast_f32_k2<7>(tile, g, ph, Tu, tid); break;
   }
 }
 void emu_fast_slot(double2*, int, const HqGateDesc*, const HqPassHeader&, int, int) {}

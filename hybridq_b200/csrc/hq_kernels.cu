@@ -81,16 +81,11 @@ __device__ __forceinline__ void rowpair_dispatch(float4*, const HqGateDesc*, uin
 
 template <int S, int MAXK>
 __device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
-                                          const unsigned char* prog, uint32_t n_gates, int Tu, int tid,
-                                          SlotTables& next) {
+                                          const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
   if (S < int(n_gates)) {
     const HqGateDesc* g = gates + S;
-    const SlotTables cur = next;
-    // fetch the next slot's lane tables now; they are consumed after this slot's barrier
-    if (S + 1 < HQ_FAST_SLOTS && S + 1 < int(n_gates) && ((ph.fast_mask >> (S + 1)) & 1u))
-      slot_tables_load(next, gates + S + 1, tid);
     if ((ph.fast_mask >> S) & 1u) {
-      gate_fast_f32_k2<S>(tile, g, ph, cur, Tu, tid);
+      gate_fast_f32_k2<S>(tile, g, ph, Tu, tid);
     } else {
       const bool low = __ldg(&g->tpos[0]) == 0;
       gate_small_generic<MAXK>(tile, g, __ldg(&g->k), low, prog, __ldg(&g->mat_off), Tu, tid);
@@ -102,17 +97,14 @@ __device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates,
 template <typename T, int MAXK>
 __device__ __forceinline__ void fast_slots(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
                                            const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
-  SlotTables next;
-  next.st = 0;
-  if (ph.fast_mask & 1u) slot_tables_load(next, gates, tid);
-  fast_slot<0, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<1, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<2, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<3, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<4, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<5, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<6, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
-  fast_slot<7, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid, next);
+  fast_slot<0, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<1, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<2, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<3, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<4, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<5, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<6, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
+  fast_slot<7, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
 }
 template <typename T, int MAXK>
 __device__ __forceinline__ void fast_slots(double2*, const HqGateDesc*, const HqPassHeader&, const unsigned char*,

@@ -181,36 +181,24 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc* __restrict__ g, const
 
 // Fast slot: the same arithmetic as gate_small_f32<2>, with the 4x4 matrix taken from the pass
 // header (kernel parameter = constant bank) at compile-time offsets, so that every FFMA has
-// only two register operands and issues at full rate.  The lane tables of a slot are fetched
-// while the previous slot is still computing (SlotTables), and each slot address is computed once
-// and reused by the load and the store.
-struct SlotTables {
-  uint32_t st;
-  uint32_t xo[4];
-};
-
-HQ_DEV void slot_tables_load(SlotTables& t, const HqGateDesc* __restrict__ g, int tid) {
-  t.st = HQ_LDG(&g->tbl_thread[tid]);
-  HQ_UNROLL
-  for (int m = 0; m < 4; ++m) t.xo[m] = HQ_LDG(&g->tbl_x[m]);
-}
-
+// only two register operands and issues at full rate.
 template <int S>
 HQ_DEV void gate_fast_f32_k2(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph,
-                             const SlotTables& t, int Tu, int tid) {
+                             int Tu, int tid) {
   const int nq = Tu - 2;
   const uint32_t nwork = 1u << nq;
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
+  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  uint32_t xo[4];
+  HQ_UNROLL
+  for (int m = 0; m < 4; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = t.st ^ uint32_t(HQ_LDG(&g->tbl_iter[it]));
-    float4* p[4];
-    HQ_UNROLL
-    for (int m = 0; m < 4; ++m) p[m] = tile + (sb ^ t.xo[m]);
+    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
     float4 in[4];
     HQ_UNROLL
-    for (int m = 0; m < 4; ++m) in[m] = *p[m];
+    for (int m = 0; m < 4; ++m) in[m] = tile[sb ^ xo[m]];
     HQ_UNROLL
     for (int i = 0; i < 4; ++i) {
       float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
@@ -220,7 +208,7 @@ HQ_DEV void gate_fast_f32_k2(float4* tile, const HqGateDesc* __restrict__ g, con
         cmac(a0r, a0i, ur, ui, in[j].x, in[j].y);
         cmac(a1r, a1i, ur, ui, in[j].z, in[j].w);
       }
-      *p[i] = make_float4(a0r, a0i, a1r, a1i);
+      tile[sb ^ xo[i]] = make_float4(a0r, a0i, a1r, a1i);
     }
   }
 }
