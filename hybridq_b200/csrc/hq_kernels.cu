@@ -21,6 +21,10 @@
 #include "hq_kernels.h"
 #include "hq_tile.cuh"
 
+#ifndef HQ_K0F_BLOCKS
+#define HQ_K0F_BLOCKS 3   // resident CTAs per SM the k <= 2 complex64 tile kernel is compiled for
+#endif
+
 namespace hq {
 
 // ---------------------------------------------------------------------------------------
@@ -111,7 +115,7 @@ __device__ __forceinline__ void fast_slots(double2*, const HqGateDesc*, const Hq
                                            uint32_t, int, int) {}
 
 template <typename T, int KCLASS, int NBUF>
-__global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 || (KCLASS == 1 && Traits<T>::V == 1)) ? 3 : 2))
+__global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 && Traits<T>::V == 1) ? HQ_K0F_BLOCKS : ((KCLASS == 0 || (KCLASS == 1 && Traits<T>::V == 1)) ? 3 : 2)))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
                const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles) {
   typedef typename Traits<T>::Unit Unit;
