@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=24, help="gate-applies per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--n", type=int, default=0, help="override the number of qubits (diagnostics only)")
+    ap.add_argument("--qubits", type=int, default=0, help="override the base number of qubits (diagnostics only)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     args = ap.parse_args()
     global N_BASE, SCALING
@@ -244,8 +244,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
-    if args.n:
-        N_BASE = args.n
+    if args.qubits:
+        N_BASE = args.qubits
     n, gates, lowered, name = workload(world)
     steps, warmup = args.steps, max(args.warmup, 3)
     state_bytes = (2 ** n) * 8
