@@ -182,6 +182,23 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc* __restrict__ g, const
 // Fast slot: the same arithmetic as gate_small_f32<2>, with the 4x4 matrix taken from the pass
 // header (kernel parameter = constant bank) at compile-time offsets, so that every FFMA has
 // only two register operands and issues at full rate.
+// acc(lo, hi) += x(lo, hi) * s  -- one FFMA2 with the scalar broadcast from a uniform register
+// (SASS: FFMA2 R, R.F32x2, UR.F32, R.F32x2).
+struct F2 { float lo, hi; };
+HQ_DEV void ffma2_bcast(F2& acc, const F2& x, float s) {
+#ifdef __CUDACC__
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x.lo), "f"(x.hi));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.lo), "f"(acc.hi));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.lo), "=f"(acc.hi) : "l"(c));
+#else
+  acc.lo = x.lo * s + acc.lo;
+  acc.hi = x.hi * s + acc.hi;
+#endif
+}
+
 template <int S>
 HQ_DEV void gate_fast_f32_k2(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph,
                              int Tu, int tid) {
@@ -196,19 +213,28 @@ HQ_DEV void gate_fast_f32_k2(float4* tile, const HqGateDesc* __restrict__ g, con
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
     const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
-    float4 in[4];
+    // amplitude pairs (re, im) of the even / odd group and the same multiplied by i: (-im, re)
+    F2 e[4], o[4], ie[4], io[4];
     HQ_UNROLL
-    for (int m = 0; m < 4; ++m) in[m] = tile[sb ^ xo[m]];
+    for (int m = 0; m < 4; ++m) {
+      const float4 v = tile[sb ^ xo[m]];
+      e[m].lo = v.x;   e[m].hi = v.y;
+      o[m].lo = v.z;   o[m].hi = v.w;
+      ie[m].lo = -v.y; ie[m].hi = v.x;
+      io[m].lo = -v.w; io[m].hi = v.z;
+    }
     HQ_UNROLL
     for (int i = 0; i < 4; ++i) {
-      float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+      F2 a0 = {0.f, 0.f}, a1 = {0.f, 0.f};
       HQ_UNROLL
       for (int j = 0; j < 4; ++j) {
         const float ur = ph.fast_u[S][2 * (i * 4 + j)], ui = ph.fast_u[S][2 * (i * 4 + j) + 1];
-        cmac(a0r, a0i, ur, ui, in[j].x, in[j].y);
-        cmac(a1r, a1i, ur, ui, in[j].z, in[j].w);
+        ffma2_bcast(a0, e[j], ur);      // (ar, ai) += ur * (xr, xi)
+        ffma2_bcast(a0, ie[j], ui);     // (ar, ai) += ui * (-xi, xr)
+        ffma2_bcast(a1, o[j], ur);
+        ffma2_bcast(a1, io[j], ui);
       }
-      tile[sb ^ xo[i]] = make_float4(a0r, a0i, a1r, a1i);
+      tile[sb ^ xo[i]] = make_float4(a0.lo, a0.hi, a1.lo, a1.hi);
     }
   }
 }
