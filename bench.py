@@ -223,6 +223,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--qubits", type=int, default=0, help="override the base number of qubits (diagnostics only)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--plan-options", default="", help="diagnostics: comma-separated PlanOptions fields "
+                    "(tile_bits,min_run_bits,fuse,max_gates_per_pass,lookahead,merge_max_k,merge_pass_cost,fast_slots,mma_min_k)")
     args = ap.parse_args()
     global N_BASE, SCALING
     SCALING = args.scaling
@@ -251,8 +253,9 @@ def main():
     state_bytes = (2 ** n) * 8
     hb.lib.hq_launch_count_reset()
 
+    plan_opts = hb.PlanOptions(*[int(x) for x in args.plan_options.split(",")]) if args.plan_options else None
     if world == 1:
-        runner = SingleGpuRunner(hb, n, lowered)
+        runner = SingleGpuRunner(hb, n, lowered, plan_opts)
     else:
         from hybridq_b200.dist import ShardedRunner
         runner = ShardedRunner(n, lowered, CTYPE, dist)
@@ -355,11 +358,11 @@ def main():
 
 
 class SingleGpuRunner:
-    def __init__(self, hb, n, lowered):
+    def __init__(self, hb, n, lowered, plan_opts=None):
         self.hb = hb
         self.n = n
         self.lowered = lowered
-        self.plan = hb.Plan(lowered, n, CTYPE)
+        self.plan = hb.Plan(lowered, n, CTYPE, plan_opts)
         self.n_gates = self.plan.n_gates
         self.local_passes = self.plan.n_passes
         self.state = hb.DeviceState(n, CTYPE)

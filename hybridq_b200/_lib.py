@@ -42,12 +42,12 @@ class PlanOptions(ctypes.Structure):
     _fields_ = [("tile_bits", ctypes.c_int), ("min_run_bits", ctypes.c_int), ("fuse", ctypes.c_int),
                 ("max_gates_per_pass", ctypes.c_int), ("lookahead", ctypes.c_int),
                 ("merge_max_k", ctypes.c_int), ("merge_pass_cost", ctypes.c_int),
-                ("fast_slots", ctypes.c_int)]
+                ("fast_slots", ctypes.c_int), ("mma_min_k", ctypes.c_int)]
 
     def __init__(self, tile_bits=0, min_run_bits=-1, fuse=1, max_gates_per_pass=0, lookahead=0,
-                 merge_max_k=-1, merge_pass_cost=-1, fast_slots=1):
+                 merge_max_k=-1, merge_pass_cost=-1, fast_slots=1, mma_min_k=-1):
         super().__init__(tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead, merge_max_k,
-                         merge_pass_cost, fast_slots)
+                         merge_pass_cost, fast_slots, mma_min_k)
 
 
 def _proto(name, restype, *argtypes):

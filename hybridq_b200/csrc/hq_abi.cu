@@ -217,6 +217,7 @@ hq::PlanOptions convert_opts(const hq_plan_options* o) {
     p.merge_max_k = o->merge_max_k;
     p.merge_pass_cost = o->merge_pass_cost;
     p.fast_slots = o->fast_slots;
+    p.mma_min_k = o->mma_min_k;
   }
   return p;
 }
@@ -325,6 +326,7 @@ int hq_apply_U_direct_dev(void* state, int dtype, unsigned int n, const void* U_
   hq::Plan plan;
   hq::PlanOptions o;
   o.fuse = 0;
+  o.mma_min_k = 0;          // the direct kernel reads the plain row-major matrix
   if (hq::plan_build(plan, dtype, n, {g}, o)) return fail(plan.error, 1);
   HqGateDesc gd;
   memcpy(&gd, plan.program.data() + plan.passes[0].header.gates_off, sizeof(gd));

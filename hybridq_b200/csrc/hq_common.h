@@ -30,17 +30,20 @@
 #define HQ_GATE_SMALL 0
 #define HQ_GATE_BIG 1
 #define HQ_GATE_ROWPAIR 2     // complex128 k = 2, 3: row-pair scheme (see HqGateDesc::tbl_rthread)
+#define HQ_GATE_MMA 3         // tensor-core path (hq_mma.cuh): mma.sync 3xTF32 / FP64, 2 <= k <= HQ_MMA_MAX_K
+#define HQ_MMA_MAX_K 6
 
 #define HQ_MAX_PER_THREAD 16   // units per thread per tile = 2^(unit bits - 8) <= 16
 #define HQ_MAX_PASS_GATES 24   // kernel matrices per pass after merging
 #define HQ_FAST_SLOTS 8        // unrolled constant-bank gate slots per pass (complex64, k = 2)
 
-struct HqGateDesc {        // 1168 bytes, lives in the device program buffer (read through L1)
+struct HqGateDesc {        // 1280 bytes, lives in the device program buffer (read through L1)
   uint32_t k;              // number of target bits
   uint32_t kind;           // HQ_GATE_SMALL / HQ_GATE_BIG / HQ_GATE_ROWPAIR
   uint32_t mat_off;        // byte offset of the matrix from the program base
                            //   small: row-major 2^k x 2^k, interleaved (re, im)
                            //   big  : column-major (transposed), interleaved
+                           //   mma  : per-lane B fragments, 16 bytes each: [(s * KS + j) * 32 + lane]
   uint32_t n_free;         // number of entries in q[]
   uint8_t tpos[16];        // ascending LOCAL amplitude-bit positions of matrix bits 0..k-1
   uint8_t q[16];           // small: ordering of the non-target local UNIT bits (work-item bit b
@@ -49,15 +52,23 @@ struct HqGateDesc {        // 1168 bytes, lives in the device program buffer (re
   // scattering at all.  Work item w = tid + (it << 8) of a gate touches the units
   //   slot(w, m) = tbl_thread[tid] ^ tbl_iter[it] ^ tbl_x[m],   m = 0 .. 2^KK - 1
   // (already swizzled shared-memory slots; swz is GF(2)-linear so the XOR composes).
+  // HQ_GATE_MMA reuses the three tables with its own lane mapping (lane = 4 g + t, see hq_mma.cuh):
+  //   slot(row set it, row g, m) = tbl_thread[tid] ^ tbl_iter[it] ^ tbl_x[m],  m = t + 4 s
+  // in units (unit path) or in float2 amplitudes (complex64 amplitude path, mma_amp = 1).
   uint16_t tbl_thread[HQ_THREADS];
   uint16_t tbl_iter[16];
-  uint16_t tbl_x[16];
+  uint16_t tbl_x[64];
   // complex128 "row-pair" scheme (k = 2, 3): thread tid = (group slot gs, row pair rp) with
   // rp = tid & (2^(k-1) - 1), gs = tid >> (k-1); the units of its group are
   //   slot(gs, it, m) = tbl_rthread[gs] ^ tbl_riter[it] ^ tbl_x[m]
   // and it produces rows 2rp, 2rp+1 of the group with those two matrix rows held in registers.
   uint16_t tbl_rthread[HQ_THREADS];
   uint16_t tbl_riter[16];
+  // HQ_GATE_MMA
+  uint32_t mma_n_iter;     // row sets per warp
+  uint32_t mma_warps;      // warps that have work (all 8 unless the tile is small)
+  uint32_t mma_amp;        // complex64: 1 = amplitude granularity (amplitude bit 0 is a target)
+  uint32_t mma_row8;       // amplitude path: XOR offset of row g + 8
 };
 
 struct HqPassHeader {      // passed to the kernel by value (constant bank)
@@ -88,5 +99,5 @@ struct HqPassHeader {      // passed to the kernel by value (constant bank)
   float fast_u[HQ_FAST_SLOTS][32];
 };
 
-static_assert(sizeof(HqGateDesc) == 624 + 512 + 32, "HqGateDesc layout");
+static_assert(sizeof(HqGateDesc) == 624 + 96 + 512 + 32 + 16, "HqGateDesc layout");
 static_assert(sizeof(HqPassHeader) == 256 + 8 + 4 * 32 * HQ_FAST_SLOTS, "HqPassHeader layout");

@@ -56,6 +56,135 @@ void emu_rowpair(double2* tile, const HqGateDesc* g, const unsigned char* prog, 
 }
 void emu_rowpair(float4*, const HqGateDesc*, const unsigned char*, int) {}
 
+// ---- tensor-core gates: the warp-collective mma.sync is modelled on whole fragment sets --------
+// (PTX fragment layouts as listed in hq_mma.cuh; tools/microbench_mma.cu checks them on the GPU).
+inline float tf32_trunc(float x) {
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  b &= 0xffffe000u;
+  memcpy(&x, &b, 4);
+  return x;
+}
+
+// D(16x8) += A(16x8) * B(8x8), operands truncated to TF32, fp32 accumulation
+void emu_mma_tf32(float (*d)[4], const float (*a)[4], const float (*b)[2]) {   // [lane][reg]
+  float A[16][8], B[8][8];
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, t = lane & 3;
+    A[g][t] = tf32_trunc(a[lane][0]); A[g + 8][t] = tf32_trunc(a[lane][1]);
+    A[g][t + 4] = tf32_trunc(a[lane][2]); A[g + 8][t + 4] = tf32_trunc(a[lane][3]);
+    B[t][g] = tf32_trunc(b[lane][0]); B[t + 4][g] = tf32_trunc(b[lane][1]);
+  }
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const int rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
+    for (int e = 0; e < 4; ++e) {
+      float acc = d[lane][e];
+      for (int kk = 0; kk < 8; ++kk) acc += A[rows[e]][kk] * B[kk][cols[e]];
+      d[lane][e] = acc;
+    }
+  }
+}
+
+// D(8x8) += A(8x4) * B(4x8) in double
+void emu_dmma(double (*d)[2], const double* a, const double* b) {   // [lane]
+  double A[8][4], B[4][8];
+  for (int lane = 0; lane < 32; ++lane) {
+    A[lane >> 2][lane & 3] = a[lane];
+    B[lane & 3][lane >> 2] = b[lane];
+  }
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int e = 0; e < 2; ++e) {
+      double acc = d[lane][e];
+      for (int kk = 0; kk < 4; ++kk) acc += A[g][kk] * B[kk][2 * t + e];
+      d[lane][e] = acc;
+    }
+  }
+}
+
+void emu_mma_gate(float4* tile, const HqGateDesc* g, const unsigned char* prog) {
+  const int KS = (1 << g->k) / 4;
+  const float4* bfr = reinterpret_cast<const float4*>(prog + g->mat_off);
+  float2* amps = reinterpret_cast<float2*>(tile);
+  for (uint32_t warp = 0; warp < g->mma_warps; ++warp)
+    for (uint32_t it = 0; it < g->mma_n_iter; ++it) {
+      std::vector<float> raw(size_t(32 * KS * 4));
+      uint32_t sb[32];
+      for (int lane = 0; lane < 32; ++lane) {
+        const int t = lane & 3;
+        sb[lane] = uint32_t(g->tbl_thread[warp * 32 + uint32_t(lane)]) ^ uint32_t(g->tbl_iter[it]);
+        for (int s = 0; s < KS; ++s) {
+          const uint32_t xo = g->tbl_x[t + 4 * s];
+          float* a = &raw[size_t((lane * KS + s) * 4)];
+          if (g->mma_amp) {
+            const float2 p = amps[sb[lane] ^ xo], q = amps[sb[lane] ^ g->mma_row8 ^ xo];
+            a[0] = p.x; a[1] = q.x; a[2] = p.y; a[3] = q.y;
+          } else {
+            const float4 v = tile[sb[lane] ^ xo];
+            a[0] = v.x; a[1] = v.z; a[2] = v.y; a[3] = v.w;
+          }
+        }
+      }
+      for (int j = 0; j < KS; ++j) {
+        float d[32][4] = {};
+        for (int s = 0; s < KS; ++s) {
+          float hi[32][4], lo[32][4], bh[32][2], bl[32][2];
+          for (int lane = 0; lane < 32; ++lane) {
+            for (int e = 0; e < 4; ++e) {
+              const float x = raw[size_t((lane * KS + s) * 4 + e)];
+              uint32_t b;                              // HQ_TF32_SPLIT 1: hi = round-to-nearest by add + mask
+              memcpy(&b, &x, 4);
+              b = (b + 0x1000u) & 0xffffe000u;
+              memcpy(&hi[lane][e], &b, 4);
+              lo[lane][e] = x - hi[lane][e];           // the tensor core truncates lo
+            }
+            const float4 b = bfr[(s * KS + j) * 32 + lane];
+            bh[lane][0] = b.x; bh[lane][1] = b.y; bl[lane][0] = b.z; bl[lane][1] = b.w;
+          }
+          emu_mma_tf32(d, lo, bh);
+          emu_mma_tf32(d, hi, bl);
+          emu_mma_tf32(d, hi, bh);
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+          const uint32_t xj = g->tbl_x[(lane & 3) + 4 * j];
+          if (g->mma_amp) {
+            amps[sb[lane] ^ xj] = make_float2(d[lane][0], d[lane][1]);
+            amps[sb[lane] ^ g->mma_row8 ^ xj] = make_float2(d[lane][2], d[lane][3]);
+          } else {
+            tile[sb[lane] ^ xj] = make_float4(d[lane][0], d[lane][1], d[lane][2], d[lane][3]);
+          }
+        }
+      }
+    }
+}
+
+void emu_mma_gate(double2* tile, const HqGateDesc* g, const unsigned char* prog) {
+  const int KS = (1 << g->k) / 4;
+  const double2* bfr = reinterpret_cast<const double2*>(prog + g->mat_off);
+  for (uint32_t warp = 0; warp < g->mma_warps; ++warp)
+    for (uint32_t it = 0; it < g->mma_n_iter; ++it) {
+      std::vector<double2> x(size_t(32 * KS));
+      uint32_t sb[32];
+      for (int lane = 0; lane < 32; ++lane) {
+        sb[lane] = uint32_t(g->tbl_thread[warp * 32 + uint32_t(lane)]) ^ uint32_t(g->tbl_iter[it]);
+        for (int s = 0; s < KS; ++s) x[size_t(lane * KS + s)] = tile[sb[lane] ^ g->tbl_x[(lane & 3) + 4 * s]];
+      }
+      for (int j = 0; j < KS; ++j) {
+        double d[32][2] = {};
+        for (int s = 0; s < KS; ++s) {
+          double a[32], b[32];
+          for (int lane = 0; lane < 32; ++lane) { a[lane] = x[size_t(lane * KS + s)].x; b[lane] = bfr[(s * KS + j) * 32 + lane].x; }
+          emu_dmma(d, a, b);
+          for (int lane = 0; lane < 32; ++lane) { a[lane] = x[size_t(lane * KS + s)].y; b[lane] = bfr[(s * KS + j) * 32 + lane].y; }
+          emu_dmma(d, a, b);
+        }
+        for (int lane = 0; lane < 32; ++lane)
+          tile[sb[lane] ^ g->tbl_x[(lane & 3) + 4 * j]] = make_double2(d[lane][0], d[lane][1]);
+      }
+    }
+}
+
 template <typename T>
 void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned char* prog, const HqPassHeader& ph) {
   typedef typename hq::Traits<T>::Unit Unit;
@@ -80,9 +209,11 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
       const HqGateDesc* g = gates + gi;
       if (V == 1 && ph.max_k <= 2 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
         for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
+      } else if (g->kind == HQ_GATE_MMA) {
+        emu_mma_gate(tile.data(), g, prog);
       } else if (V == 0 && g->kind == HQ_GATE_ROWPAIR) {
         emu_rowpair(tile.data(), g, prog, Tu);
-      } else if (g->k <= HQ_SMALL_K) {
+      } else if (g->kind != HQ_GATE_BIG) {
         const bool low = V == 1 && g->tpos[0] == 0;
         for (int tid = 0; tid < HQ_THREADS; ++tid)
           hq::gate_small_dispatch<4>(tile.data(), g, g->k, low, prog, g->mat_off, Tu, tid);
@@ -141,6 +272,7 @@ hq::PlanOptions make_opts(const int* o) {
     p.merge_max_k = o[5];
     p.merge_pass_cost = o[6];
     p.fast_slots = o[7];
+    p.mma_min_k = o[8];
   }
   return p;
 }
@@ -150,8 +282,8 @@ hq::PlanOptions make_opts(const int* o) {
 extern "C" {
 
 // opts = {tile_bits, min_run_bits, fuse, max_gates_per_pass, lookahead, merge_max_k, merge_pass_cost,
-// fast_slots} or NULL.
-// info_out (optional, >= 2 ints) receives {n_passes, n_gates}.
+// fast_slots, mma_min_k} or NULL.
+// info_out (optional, >= 4 ints) receives {n_passes, n_gates, n_kernel_gates, n_mma_gates}.
 int hq_emu_run_circuit(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
                        const double* U_flat, const int* opts, void* state_interleaved, int* info_out,
                        char* err, int err_len) {
@@ -177,6 +309,10 @@ int hq_emu_run_circuit(int dtype, unsigned n, unsigned n_gates, const unsigned* 
     info_out[0] = int(plan.passes.size());
     info_out[1] = int(plan.n_gates);
     info_out[2] = int(plan.n_kernel_gates);
+    int n_mma = 0;
+    for (unsigned i = 0; i < plan.n_kernel_gates; ++i)
+      n_mma += reinterpret_cast<const HqGateDesc*>(plan.program.data())[i].kind == HQ_GATE_MMA;
+    info_out[3] = n_mma;
   }
   return 0;
 }

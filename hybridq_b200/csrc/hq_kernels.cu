@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "hq_kernels.h"
+#include "hq_mma.cuh"
 #include "hq_tile.cuh"
 
 #ifndef HQ_K0F_BLOCKS
@@ -64,12 +65,106 @@ __device__ __forceinline__ void tile_fill(typename Traits<T>::Unit* tile,
   for (int i = 0; i < npt; ++i) cp_async16(&tile[swz_t ^ ph.iter_swz[i]], src + ph.iter_off[i]);
 }
 
-// One out-of-line copy of the generic register path per kernel (it is called from the unrolled
-// fast-slot sequence as well as from the tail loop).
-template <int MAXK, typename Unit>
-__device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g, uint32_t k, bool low,
-                                                const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
-  gate_small_dispatch<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
+// ---------------------------------------------------------------------------------------
+// tensor-core gates (HQ_GATE_MMA): table-driven addressing around the loops of hq_mma.cuh.
+// A warp owns row sets it = 0 .. mma_n_iter-1 (UNR of them in flight at a time); warps beyond
+// mma_warps have no rows (small tiles only) and skip the gate as a whole, so every mma.sync
+// is executed by full warps.
+// ---------------------------------------------------------------------------------------
+template <int KS, int UNR>
+__device__ __forceinline__ void gate_mma_rows_f32(float4* tile, const HqGateDesc* __restrict__ g, uint32_t st,
+                                                  uint32_t n_iter, bool amp, uint32_t row8, const uint32_t (&xo)[KS],
+                                                  const float4* __restrict__ bf, const float4* breg,
+                                                  const uint16_t* __restrict__ xtab) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < n_iter; it += UNR) {
+    uint32_t sb[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
+    if (amp)
+      mma_iter_f32_amp<KS, UNR, (KS <= 2), (KS >= 16)>(reinterpret_cast<float2*>(tile), sb, row8, xo, bf, breg, xtab);
+    else
+      mma_iter_f32_unit<KS, UNR, (KS <= 2), (KS >= 16)>(tile, sb, xo, bf, breg, xtab);
+  }
+}
+
+template <int KS, int UNR>
+__device__ __forceinline__ void gate_mma(float4* tile, const HqGateDesc* __restrict__ g,
+                                         const unsigned char* __restrict__ prog, int tid) {
+  const int lane = tid & 31, t = lane & 3;
+  if (uint32_t(tid >> 5) >= __ldg(&g->mma_warps)) return;
+  const uint32_t st = __ldg(&g->tbl_thread[tid]);
+  const uint32_t n_iter = __ldg(&g->mma_n_iter);
+  const bool amp = __ldg(&g->mma_amp) != 0;
+  const uint32_t row8 = __ldg(&g->mma_row8);
+  uint32_t xo[KS];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) xo[s] = __ldg(&g->tbl_x[t + 4 * s]);
+  const float4* bf = reinterpret_cast<const float4*>(prog + __ldg(&g->mat_off)) + lane;
+  float4 breg[KS <= 2 ? KS * KS : 1];
+  if (KS <= 2) {
+#pragma unroll
+    for (int e = 0; e < KS * KS; ++e) breg[e] = __ldg(&bf[e * 32]);
+  }
+  const uint16_t* xtab = &g->tbl_x[t];
+  if (UNR > 1 && n_iter >= uint32_t(UNR))
+    gate_mma_rows_f32<KS, UNR>(tile, g, st, n_iter, amp, row8, xo, bf, breg, xtab);
+  else
+    gate_mma_rows_f32<KS, 1>(tile, g, st, n_iter, amp, row8, xo, bf, breg, xtab);
+}
+
+template <int KS, int UNR>
+__device__ __forceinline__ void gate_mma_rows_f64(double2* tile, const HqGateDesc* __restrict__ g, uint32_t st,
+                                                  uint32_t n_iter, const uint32_t (&xo)[KS],
+                                                  const double2* __restrict__ bf, const double2* breg,
+                                                  const uint16_t* __restrict__ xtab) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < n_iter; it += UNR) {
+    uint32_t sb[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
+    dmma_iter_f64<KS, UNR, (KS <= 2)>(tile, sb, xo, bf, breg, xtab);
+  }
+}
+
+template <int KS, int UNR>
+__device__ __forceinline__ void gate_mma(double2* tile, const HqGateDesc* __restrict__ g,
+                                         const unsigned char* __restrict__ prog, int tid) {
+  const int lane = tid & 31, t = lane & 3;
+  if (uint32_t(tid >> 5) >= __ldg(&g->mma_warps)) return;
+  const uint32_t st = __ldg(&g->tbl_thread[tid]);
+  const uint32_t n_iter = __ldg(&g->mma_n_iter);
+  uint32_t xo[KS];
+#pragma unroll
+  for (int s = 0; s < KS; ++s) xo[s] = __ldg(&g->tbl_x[t + 4 * s]);
+  const double2* bf = reinterpret_cast<const double2*>(prog + __ldg(&g->mat_off)) + lane;
+  double2 breg[KS <= 2 ? KS * KS : 1];
+  if (KS <= 2) {
+#pragma unroll
+    for (int e = 0; e < KS * KS; ++e) breg[e] = __ldg(&bf[e * 32]);
+  }
+  const uint16_t* xtab = &g->tbl_x[t];
+  if (UNR > 1 && n_iter >= uint32_t(UNR))
+    gate_mma_rows_f64<KS, UNR>(tile, g, st, n_iter, xo, bf, breg, xtab);
+  else
+    gate_mma_rows_f64<KS, 1>(tile, g, st, n_iter, xo, bf, breg, xtab);
+}
+
+template <typename Unit> struct IsF64Unit { static const bool value = false; };
+template <> struct IsF64Unit<double2> { static const bool value = true; };
+
+// MMAK: largest k the kernel class can meet (2, 3, 4 or HQ_MMA_MAX_K)
+template <int MMAK, typename Unit>
+__device__ __forceinline__ void gate_mma_dispatch(Unit* tile, const HqGateDesc* g, uint32_t k,
+                                                  const unsigned char* prog, int tid) {
+  switch (k) {
+    case 2: gate_mma<1, 2>(tile, g, prog, tid); break;
+    case 3: if (MMAK >= 3) gate_mma<2, IsF64Unit<Unit>::value ? 1 : 2>(tile, g, prog, tid); break;
+    case 4: if (MMAK >= 4) gate_mma<4, 1>(tile, g, prog, tid); break;
+    case 5: if (MMAK >= 5) gate_mma<8, 1>(tile, g, prog, tid); break;
+    case 6: if (MMAK >= 6) gate_mma<16, 1>(tile, g, prog, tid); break;
+    default: break;
+  }
 }
 
 template <int MAXK>
@@ -83,6 +178,22 @@ template <int MAXK>
 __device__ __forceinline__ void rowpair_dispatch(float4*, const HqGateDesc*, uint32_t, const unsigned char*, uint32_t,
                                                  int, int) {}
 
+// One out-of-line copy per kernel of everything but the two-phase path: the register paths, the
+// complex128 row-pair scheme and the tensor-core path (it is called from the unrolled fast-slot
+// sequence as well as from the gate loop).
+template <int MAXK, int MMAK, typename Unit>
+__device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g, uint32_t k, uint32_t kind,
+                                                const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
+  if (kind == HQ_GATE_MMA) {
+    gate_mma_dispatch<MMAK>(tile, g, k, prog, tid);
+  } else if (IsF64Unit<Unit>::value && kind == HQ_GATE_ROWPAIR) {
+    rowpair_dispatch<MAXK>(tile, g, k, prog, mat_off, Tu, tid);
+  } else {
+    const bool low = !IsF64Unit<Unit>::value && __ldg(&g->tpos[0]) == 0;
+    gate_small_dispatch<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
+  }
+}
+
 template <int S, int MAXK>
 __device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
                                           const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
@@ -91,8 +202,7 @@ __device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates,
     if ((ph.fast_mask >> S) & 1u) {
       gate_fast_f32_k2<S>(tile, g, ph, Tu, tid);
     } else {
-      const bool low = __ldg(&g->tpos[0]) == 0;
-      gate_small_generic<MAXK>(tile, g, __ldg(&g->k), low, prog, __ldg(&g->mat_off), Tu, tid);
+      gate_small_generic<MAXK, MAXK>(tile, g, __ldg(&g->k), __ldg(&g->kind), prog, __ldg(&g->mat_off), Tu, tid);
     }
     __syncthreads();
   }
@@ -122,6 +232,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
   typedef typename Traits<T>::Cplx Cplx;
   const int V = Traits<T>::V;
   const int MAXK = KCLASS == 0 ? 2 : (KCLASS == 1 ? 3 : 4);
+  const int MMAK = KCLASS == 3 ? HQ_MMA_MAX_K : MAXK;
   extern __shared__ __align__(16) unsigned char smem[];
 
   const int tid = threadIdx.x;
@@ -175,11 +286,9 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
       const HqGateDesc* g = gates + gi;
       const uint32_t k = __ldg(&g->k);
       const uint32_t mat_off = __ldg(&g->mat_off);
-      if (V == 0 && __ldg(&g->kind) == HQ_GATE_ROWPAIR) {
-        rowpair_dispatch<MAXK>(tile, g, k, prog, mat_off, Tu, tid);
-      } else if (KCLASS < 3 || k <= HQ_SMALL_K) {
-        const bool low = V == 1 && __ldg(&g->tpos[0]) == 0;
-        gate_small_generic<MAXK>(tile, g, k, low, prog, mat_off, Tu, tid);
+      const uint32_t kind = __ldg(&g->kind);
+      if (KCLASS < 3 || kind != HQ_GATE_BIG) {
+        gate_small_generic<MAXK, MMAK>(tile, g, k, kind, prog, mat_off, Tu, tid);
       } else {
         const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + mat_off);
         const int rounds = big_rounds(Tbits, int(k));

@@ -52,9 +52,10 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 //   1  hi = round-to-nearest by integer add + mask, lo = x - hi: 3 instructions
 //   2  hi = cvt.rna.tf32.f32 (ptxas expands it to 4 instructions with an inf/nan guard), lo = x - hi
 // lo always goes to the tensor core as raw fp32 bits.  Relative error per product: about 2^-20
-// (SPLIT 0) or 2^-21 (1, 2); profiles/r01/microbench_mma.jsonl has the measured errors.
+// (SPLIT 0) or 2^-21 (1, 2).  Measured on B200 (profiles/r01/microbench_mma_b.jsonl, 16 k = 2 gates
+// on a tile): max-abs error 3.6e-7 (SPLIT 0) vs 1.2e-7 (SPLIT 1) at the same speed, so 1 is the default.
 #ifndef HQ_TF32_SPLIT
-#define HQ_TF32_SPLIT 0
+#define HQ_TF32_SPLIT 1
 #endif
 template <int SPLIT>
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
@@ -77,128 +78,160 @@ __device__ __forceinline__ void unit_to_afrag(const float4& v, float (&a)[4]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// complex64, UNIT granularity (amplitude bit 0 is not a target): one warp-iteration handles 8
-// unit-groups = 16 groups.  KS = 2^k / 4 k-steps and as many n-tiles.
-//   tile   shared-memory tile of float4 units
-//   sb     slot of (row g, m = 0) for this lane and iteration
-//   xo[s]  XOR offset of unit m = 4 s + t
-//   bf     B fragments of this lane: bf[(s * KS + j) * 32] = (b0_hi, b1_hi, b0_lo, b1_lo) of
-//          block (k-step s, n-tile j); BREG = already in registers (breg[s * KS + j])
-// ------------------------------------------------------------------------------------------
+// Common shape of the three gate loops below.  One call handles UNR independent row sets (UNR
+// warp-iterations) so that their shared-memory loads, mma chains and stores overlap; KS = 2^k / 4
+// k-steps and as many n-tiles.
+//   sb[u]  slot of (row g, m = 0) of row set u for this lane
+//   xo[s]  XOR offset of amplitude/unit m = 4 s + t
+//   bf     B fragments of this lane: bf[(s * KS + j) * 32] = block (k-step s, n-tile j);
+//          BREG = they are already in registers (breg[s * KS + j])
 //   xtab   &tbl_x[t]: the n-tile loop of the larger gates (KS >= 8) is kept rolled (code size,
 //          registers), so the store offset of n-tile j is re-read from the table: xtab[4 j]
-template <int KS, bool BREG, bool FLY, int SPLIT = HQ_TF32_SPLIT>
-__device__ __forceinline__ void mma_iter_f32_unit(float4* tile, uint32_t sb, const uint32_t (&xo)[KS],
+// ------------------------------------------------------------------------------------------
+
+// complex64, UNIT granularity (amplitude bit 0 is not a target): a row set is 8 unit-groups = 16
+// groups; B fragment = (b0_hi, b1_hi, b0_lo, b1_lo).
+template <int KS, int UNR, bool BREG, bool FLY, int SPLIT = HQ_TF32_SPLIT>
+__device__ __forceinline__ void mma_iter_f32_unit(float4* tile, const uint32_t (&sb)[UNR], const uint32_t (&xo)[KS],
                                                   const float4* __restrict__ bf, const float4* breg,
                                                   const uint16_t* __restrict__ xtab) {
-  float raw[KS][4];
-  uint32_t hi[FLY ? 1 : KS][4], lo[FLY ? 1 : KS][4];
+  float raw[UNR][FLY ? KS : 1][4];
+  uint32_t hi[UNR][FLY ? 1 : KS][4], lo[UNR][FLY ? 1 : KS][4];
 #pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const float4 v = tile[sb ^ xo[s]];
-    unit_to_afrag(v, raw[s]);
-    if (!FLY) {
+  for (int u = 0; u < UNR; ++u)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[s][e], hi[s][e], lo[s][e]);
+    for (int s = 0; s < KS; ++s) {
+      const float4 v = tile[sb[u] ^ xo[s]];
+      float a[4];
+      unit_to_afrag(v, a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (FLY) raw[u][s][e] = a[e];
+        else tf32_split<SPLIT>(a[e], hi[u][s][e], lo[u][s][e]);
+      }
     }
-  }
 #pragma unroll(KS >= 8 ? 1 : KS)
   for (int j = 0; j < KS; ++j) {
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    float d[UNR][4];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       const float4 b = BREG ? breg[(KS >= 8 ? 0 : s * KS + j)] : __ldg(&bf[(s * KS + j) * 32]);
       const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
       const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
       if (FLY) {
-        uint32_t h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[s][e], h[e], l[e]);
-        mma_tf32(d, l, bh0, bh1);
-        mma_tf32(d, h, bl0, bl1);
-        mma_tf32(d, h, bh0, bh1);
+        for (int u = 0; u < UNR; ++u) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[u][s][e], h[e], l[e]);
+          mma_tf32(d[u], l, bh0, bh1);
+          mma_tf32(d[u], h, bl0, bl1);
+          mma_tf32(d[u], h, bh0, bh1);
+        }
       } else {
-        mma_tf32(d, lo[s], bh0, bh1);
-        mma_tf32(d, hi[s], bl0, bl1);
-        mma_tf32(d, hi[s], bh0, bh1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], lo[u][s], bh0, bh1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bl0, bl1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bh0, bh1);
       }
     }
     const uint32_t xj = KS >= 8 ? uint32_t(__ldg(&xtab[4 * j])) : xo[KS >= 8 ? 0 : j];
-    tile[sb ^ xj] = make_float4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) tile[sb[u] ^ xj] = make_float4(d[u][0], d[u][1], d[u][2], d[u][3]);
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// complex64, AMPLITUDE granularity (any targets, used when amplitude bit 0 is a target): rows g
-// and g+8 are two different groups; `tile` is viewed as float2 amplitudes, sb0 / sb1 are the
-// float2 slots of (row g, m = 0) / (row g+8, m = 0), xo[s] the XOR offset of amplitude 4 s + t.
-// ------------------------------------------------------------------------------------------
-template <int KS, bool BREG, bool FLY, int SPLIT = HQ_TF32_SPLIT>
-__device__ __forceinline__ void mma_iter_f32_amp(float2* tile, uint32_t sb0, uint32_t sb1, const uint32_t (&xo)[KS],
-                                                 const float4* __restrict__ bf, const float4* breg,
-                                                 const uint16_t* __restrict__ xtab) {
-  float raw[KS][4];
-  uint32_t hi[FLY ? 1 : KS][4], lo[FLY ? 1 : KS][4];
+// complex64, AMPLITUDE granularity (any targets; used when amplitude bit 0 is a target): a row set
+// is 16 groups, rows g and g+8 being two different groups; `tile` is viewed as float2 amplitudes,
+// sb[u] is the float2 slot of (row g, m = 0), sb[u] ^ row8 that of (row g+8, m = 0).
+template <int KS, int UNR, bool BREG, bool FLY, int SPLIT = HQ_TF32_SPLIT>
+__device__ __forceinline__ void mma_iter_f32_amp(float2* tile, const uint32_t (&sb)[UNR], uint32_t row8,
+                                                 const uint32_t (&xo)[KS], const float4* __restrict__ bf,
+                                                 const float4* breg, const uint16_t* __restrict__ xtab) {
+  float raw[UNR][FLY ? KS : 1][4];
+  uint32_t hi[UNR][FLY ? 1 : KS][4], lo[UNR][FLY ? 1 : KS][4];
 #pragma unroll
-  for (int s = 0; s < KS; ++s) {
-    const float2 p = tile[sb0 ^ xo[s]];
-    const float2 q = tile[sb1 ^ xo[s]];
-    raw[s][0] = p.x; raw[s][1] = q.x; raw[s][2] = p.y; raw[s][3] = q.y;
-    if (!FLY) {
+  for (int u = 0; u < UNR; ++u)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[s][e], hi[s][e], lo[s][e]);
+    for (int s = 0; s < KS; ++s) {
+      const float2 p = tile[sb[u] ^ xo[s]];
+      const float2 q = tile[sb[u] ^ row8 ^ xo[s]];
+      const float a[4] = {p.x, q.x, p.y, q.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (FLY) raw[u][s][e] = a[e];
+        else tf32_split<SPLIT>(a[e], hi[u][s][e], lo[u][s][e]);
+      }
     }
-  }
 #pragma unroll(KS >= 8 ? 1 : KS)
   for (int j = 0; j < KS; ++j) {
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    float d[UNR][4];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       const float4 b = BREG ? breg[(KS >= 8 ? 0 : s * KS + j)] : __ldg(&bf[(s * KS + j) * 32]);
       const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
       const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
       if (FLY) {
-        uint32_t h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[s][e], h[e], l[e]);
-        mma_tf32(d, l, bh0, bh1);
-        mma_tf32(d, h, bl0, bl1);
-        mma_tf32(d, h, bh0, bh1);
+        for (int u = 0; u < UNR; ++u) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[u][s][e], h[e], l[e]);
+          mma_tf32(d[u], l, bh0, bh1);
+          mma_tf32(d[u], h, bl0, bl1);
+          mma_tf32(d[u], h, bh0, bh1);
+        }
       } else {
-        mma_tf32(d, lo[s], bh0, bh1);
-        mma_tf32(d, hi[s], bl0, bl1);
-        mma_tf32(d, hi[s], bh0, bh1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], lo[u][s], bh0, bh1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bl0, bl1);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bh0, bh1);
       }
     }
     const uint32_t xj = KS >= 8 ? uint32_t(__ldg(&xtab[4 * j])) : xo[KS >= 8 ? 0 : j];
-    tile[sb0 ^ xj] = make_float2(d[0], d[1]);
-    tile[sb1 ^ xj] = make_float2(d[2], d[3]);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      tile[sb[u] ^ xj] = make_float2(d[u][0], d[u][1]);
+      tile[sb[u] ^ row8 ^ xj] = make_float2(d[u][2], d[u][3]);
+    }
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// complex128 (unit = amplitude): one warp-iteration handles 8 groups.  One 16-byte load feeds two
-// k-steps (the re column and the im column of amplitude 4 s + t).
-//   bf[(s * KS + j) * 32] = (b of the re step, b of the im step) of block (s, j)
-// ------------------------------------------------------------------------------------------
-template <int KS, bool BREG>
-__device__ __forceinline__ void dmma_iter_f64(double2* tile, uint32_t sb, const uint32_t (&xo)[KS],
+// complex128 (unit = amplitude): a row set is 8 groups.  One 16-byte load feeds two k-steps (the
+// re column and the im column of amplitude 4 s + t); B fragment = (b of the re step, b of the im step).
+template <int KS, int UNR, bool BREG>
+__device__ __forceinline__ void dmma_iter_f64(double2* tile, const uint32_t (&sb)[UNR], const uint32_t (&xo)[KS],
                                               const double2* __restrict__ bf, const double2* breg,
                                               const uint16_t* __restrict__ xtab) {
-  double2 x[KS];
+  double2 x[UNR][KS];
 #pragma unroll
-  for (int s = 0; s < KS; ++s) x[s] = tile[sb ^ xo[s]];
+  for (int u = 0; u < UNR; ++u)
+#pragma unroll
+    for (int s = 0; s < KS; ++s) x[u][s] = tile[sb[u] ^ xo[s]];
 #pragma unroll(KS >= 8 ? 1 : KS)
   for (int j = 0; j < KS; ++j) {
-    double d0 = 0., d1 = 0.;
+    double d0[UNR], d1[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) d0[u] = d1[u] = 0.;
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       const double2 b = BREG ? breg[(KS >= 8 ? 0 : s * KS + j)] : __ldg(&bf[(s * KS + j) * 32]);
-      dmma(d0, d1, x[s].x, b.x);
-      dmma(d0, d1, x[s].y, b.y);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) dmma(d0[u], d1[u], x[u][s].x, b.x);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) dmma(d0[u], d1[u], x[u][s].y, b.y);
     }
     const uint32_t xj = KS >= 8 ? uint32_t(__ldg(&xtab[4 * j])) : xo[KS >= 8 ? 0 : j];
-    tile[sb ^ xj] = make_double2(d0, d1);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) tile[sb[u] ^ xj] = make_double2(d0[u], d1[u]);
   }
 }
 

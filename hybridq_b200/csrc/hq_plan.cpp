@@ -12,6 +12,9 @@ namespace hq {
 int default_tile_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 13 : 12; }
 int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 5; }
 int default_merge_max_k(int) { return 2; }
+// Measured on B200 (profiles/r01/microbench_mma_b.jsonl): the tensor-core path beats the FMA
+// paths for every k >= 3 (complex64) and k >= 2 (complex128).
+int default_mma_min_k(int dtype) { return dtype == HQ_DTYPE_C64 ? 3 : 2; }
 
 namespace {
 
@@ -124,6 +127,143 @@ void make_rowpair_tables(HqGateDesc& gd, int Tu) {
   const int niter = 1 << (nq - tb);
   for (int it = 0; it < 16; ++it)
     gd.tbl_riter[it] = it < niter ? uint16_t(swz(scatter_bits(uint32_t(it), gd.q, tb, nq))) : uint16_t(0);
+}
+
+// ---- tensor-core gates (HQ_GATE_MMA, device side in hq_mma.cuh) -------------------------------
+// Lane (g, t) = (lane >> 2, lane & 3) of a warp owns row g of a row set (8 rows; the complex64
+// amplitude path adds row g + 8) and the amplitudes / units m = t + 4 s of that row.  The two
+// matrix-index bits carried by t ("lane bits") and the lowest row bits are chosen so that a
+// quarter-warp of 16-byte accesses (half-warp of 8-byte accesses on the amplitude path) hits
+// distinct bank groups under swz: their unit bits must have distinct residues mod 3.
+struct MmaLayout {
+  bool amp = false;                 // complex64 amplitude granularity
+  int forder[HQ_MMA_MAX_K] = {0};   // fragment-index bit b <-> matrix-index bit forder[b]
+  std::vector<unsigned> rows;       // row bits in work-item order (local unit bits, or amplitude bits if amp)
+  int row_lane_bits = 3;            // 3 (8 rows) or 4 (16 rows: g and the g + 8 half)
+  int warp_bits = 0, iter_bits = 0;
+};
+
+bool mma_layout(const uint8_t* tpos, int k, int Tbits, int V, MmaLayout& L) {
+  if (k < 2 || k > HQ_MMA_MAX_K) return false;
+  L.amp = V == 1 && tpos[0] == 0;
+  const int bits = L.amp ? Tbits : Tbits - V;          // index bits of the granularity in use
+  std::vector<int> tb(size_t(k), 0);                   // target bits at that granularity
+  for (int i = 0; i < k; ++i) tb[size_t(i)] = L.amp ? int(tpos[i]) : int(tpos[i]) - V;
+  auto res = [&](int b) { return ((L.amp ? b - 1 : b) % 3 + 3) % 3; };   // residue of the unit bit
+  // lane bits
+  int c0 = 0, c1 = 1;
+  if (!L.amp) {
+    bool found = false;
+    for (int i = 0; i < k && !found; ++i)
+      for (int j = i + 1; j < k && !found; ++j)
+        if (res(tb[size_t(i)]) != res(tb[size_t(j)])) { c0 = i; c1 = j; found = true; }
+  }
+  int nf = 0;
+  L.forder[nf++] = c0;
+  L.forder[nf++] = c1;
+  for (int i = 0; i < k; ++i)
+    if (i != c0 && i != c1) L.forder[nf++] = i;
+  // row bits
+  std::vector<unsigned> freeb;
+  std::vector<bool> is_t(size_t(bits), false);
+  for (int i = 0; i < k; ++i) is_t[size_t(tb[size_t(i)])] = true;
+  for (int b = 0; b < bits; ++b)
+    if (!is_t[size_t(b)]) freeb.push_back(unsigned(b));
+  L.row_lane_bits = L.amp ? 4 : 3;
+  if (int(freeb.size()) < L.row_lane_bits) return false;
+  std::vector<int> avoid;
+  if (L.amp) avoid.push_back(res(tb[size_t(c1)]));
+  else { avoid.push_back(res(tb[size_t(c0)])); avoid.push_back(res(tb[size_t(c1)])); }
+  const int want = L.amp ? 2 : 1;
+  for (int c = 0; c < want; ++c)
+    for (size_t i = size_t(c); i < freeb.size(); ++i) {
+      const int r = res(int(freeb[i]));
+      if (std::find(avoid.begin(), avoid.end(), r) == avoid.end()) {
+        const unsigned b = freeb[i];
+        freeb.erase(freeb.begin() + long(i));
+        freeb.insert(freeb.begin() + c, b);
+        avoid.push_back(r);
+        break;
+      }
+    }
+  L.rows = freeb;
+  const int nrow = int(freeb.size());
+  L.warp_bits = std::min(HQ_THREADS_LOG2 - 5, nrow - L.row_lane_bits);
+  L.iter_bits = nrow - L.row_lane_bits - L.warp_bits;
+  return L.iter_bits <= 4;
+}
+
+uint32_t mma_slot(const MmaLayout& L, uint32_t x) {
+  return L.amp ? ((swz(x >> 1) << 1) | (x & 1u)) : swz(x);
+}
+
+size_t mma_mat_index(const MmaLayout& L, int k, uint32_t m) {
+  size_t r = 0;
+  for (int b = 0; b < k; ++b) r |= size_t((m >> b) & 1u) << L.forder[b];
+  return r;
+}
+
+void make_mma_tables(HqGateDesc& gd, const MmaLayout& L, int V) {
+  const int k = int(gd.k);
+  auto scat = [&](uint32_t w, int from) {
+    uint32_t u = 0;
+    for (size_t i = 0; size_t(from) + i < L.rows.size(); ++i) u |= ((w >> i) & 1u) << L.rows[size_t(from) + i];
+    return u;
+  };
+  const uint32_t wmask = (1u << L.warp_bits) - 1u;
+  for (int tid = 0; tid < HQ_THREADS; ++tid) {
+    const uint32_t lane = uint32_t(tid) & 31u, warp = uint32_t(tid) >> 5, g = lane >> 2;
+    gd.tbl_thread[tid] = uint16_t(mma_slot(L, scat(g | ((warp & wmask) << L.row_lane_bits), 0)));
+  }
+  gd.mma_n_iter = 1u << L.iter_bits;
+  gd.mma_warps = 1u << L.warp_bits;
+  gd.mma_amp = L.amp ? 1u : 0u;
+  for (uint32_t it = 0; it < 16; ++it)
+    gd.tbl_iter[it] = it < gd.mma_n_iter ? uint16_t(mma_slot(L, scat(it, L.row_lane_bits + L.warp_bits))) : uint16_t(0);
+  for (uint32_t m = 0; m < 64; ++m) {
+    uint32_t x = 0;
+    if (m < (1u << k))
+      for (int b = 0; b < k; ++b) x |= ((m >> b) & 1u) << (L.amp ? int(gd.tpos[L.forder[b]]) : int(gd.tpos[L.forder[b]]) - V);
+    gd.tbl_x[m] = uint16_t(mma_slot(L, x));
+  }
+  gd.mma_row8 = L.amp ? mma_slot(L, 1u << L.rows[3]) : 0u;
+}
+
+float tf32_rna_host(float x) {
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  b = (b + 0x1000u) & 0xffffe000u;
+  float r;
+  memcpy(&r, &b, 4);
+  return r;
+}
+
+size_t mma_frag_bytes(unsigned k) { return size_t(32) << (2 * k); }   // KS^2 blocks x 32 lanes x 16 B
+
+// B fragments (see hq_mma.cuh): block (k-step s, n-tile j), lane (g, t): input amplitude m = 4 s + t,
+// output amplitude 4 j + (g >> 1), output component re / im = g & 1;
+//   b0 = B[re(m)][n], b1 = B[im(m)][n]   with   B = [[Ur, Ui], [-Ui, Ur]]  (rows re/im in, columns re/im out)
+void write_mma_fragments(std::vector<unsigned char>& prog, size_t off, const Canon& c, const MmaLayout& L, int dtype) {
+  const int k = int(c.k);
+  const size_t dim = size_t(1) << k;
+  const int KS = int(dim / 4);
+  for (int s = 0; s < KS; ++s)
+    for (int j = 0; j < KS; ++j)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3, odd = g & 1;
+        const size_t mi = mma_mat_index(L, k, uint32_t(4 * s + t)), mo = mma_mat_index(L, k, uint32_t(4 * j + (g >> 1)));
+        const std::complex<double> u = c.U[mo * dim + mi];
+        const double b0 = odd ? u.imag() : u.real(), b1 = odd ? u.real() : -u.imag();
+        unsigned char* dst = prog.data() + off + (size_t(s * KS + j) * 32 + size_t(lane)) * 16;
+        if (dtype == HQ_DTYPE_C64) {
+          const float h0 = tf32_rna_host(float(b0)), h1 = tf32_rna_host(float(b1));
+          const float f[4] = {h0, h1, tf32_rna_host(float(b0 - double(h0))), tf32_rna_host(float(b1 - double(h1)))};
+          memcpy(dst, f, 16);
+        } else {
+          const double d[2] = {b0, b1};
+          memcpy(dst, d, 16);
+        }
+      }
 }
 
 int local_bit(const HqPassHeader& ph, unsigned global_bit) {
@@ -340,16 +480,48 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   }
 
   // ---- merge inside each pass, then serialise
-  const int merge_max_k = opts.merge_max_k < 0 ? default_merge_max_k(dtype) : std::min(opts.merge_max_k, HQ_SMALL_K);
-  const int merge_pass_cost = opts.merge_pass_cost < 0 ? 12 : opts.merge_pass_cost;
+  const int mma_min_k = opts.mma_min_k < 0 ? default_mma_min_k(dtype) : opts.mma_min_k;
+  const bool mma_on = mma_min_k >= 2;
+  // Measured on B200 (profiles/r01/sweep_mma_a.jsonl, benchmark circuit): complex128 is fastest with the
+  // tensor-core path for every k >= 2 and merging up to k = 3 (a merged k = 3 DMMA matrix costs ~1.9x a
+  // k = 2 one: merge_pass_cost 2); complex64 keeps merging at k <= 2, where the constant-bank FFMA2 slots
+  // still beat 3xTF32 (127 vs 160 ms/step), and uses the tensor cores for the k >= 3 gates it is given.
+  const int merge_default = (mma_on && dtype == HQ_DTYPE_C128) ? 3 : default_merge_max_k(dtype);
+  const int merge_max_k = opts.merge_max_k < 0 ? merge_default : std::min(opts.merge_max_k, HQ_SMALL_K);
+  const int merge_pass_cost = opts.merge_pass_cost < 0 ? ((mma_on && dtype == HQ_DTYPE_C128) ? 2 : 12) : opts.merge_pass_cost;
   std::vector<std::vector<Cluster>> merged(drafts.size());
+  std::vector<PassInfo> infos(drafts.size());
+  struct GateLayout { bool mma = false; MmaLayout L; uint8_t tpos[16] = {0}; size_t bytes = 0; };
+  std::vector<std::vector<GateLayout>> layouts(drafts.size());
   size_t total_gates = 0;
   size_t mat_bytes = 0;
   const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
   for (size_t d = 0; d < drafts.size(); ++d) {
     merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost);
     total_gates += merged[d].size();
-    for (const Cluster& c : merged[d]) mat_bytes += ((esz << (2 * c.gate.k)) + 15) & ~size_t(15);
+    // single gates may use shorter runs than the fuser is allowed to create
+    const int L = choose_run_bits(drafts[d].bits, T, drafts[d].ids.size() > 1 ? fuse_min_run : hard_min_run);
+    if (L < 0) { plan.error = "internal: pass does not fit"; return 1; }
+    PassInfo& pi = infos[d];
+    make_tile(drafts[d].bits, T, L, n, pi.header);
+    make_iter_tables(pi.header, V);
+    const int Tbits = int(pi.header.tile_bits);
+    layouts[d].resize(merged[d].size());
+    for (size_t ci = 0; ci < merged[d].size(); ++ci) {
+      const Canon& c = merged[d][ci].gate;
+      GateLayout& gl = layouts[d][ci];
+      for (unsigned i = 0; i < c.k; ++i) {
+        const int lb = local_bit(pi.header, c.pos[i]);
+        if (lb < 0) { plan.error = "internal: target bit outside tile"; return 1; }
+        gl.tpos[i] = uint8_t(lb);
+      }
+      // a lone k <= 2 gate keeps its plain matrix: such passes go to the direct kernel (hq_abi.cu)
+      const bool lone_small = merged[d].size() == 1 && c.k <= 2;
+      gl.mma = mma_on && !lone_small && int(c.k) >= mma_min_k && int(c.k) <= HQ_MMA_MAX_K &&
+               mma_layout(gl.tpos, int(c.k), Tbits, V, gl.L);
+      gl.bytes = gl.mma ? mma_frag_bytes(c.k) : (((esz << (2 * c.k)) + 15) & ~size_t(15));
+      mat_bytes += gl.bytes;
+    }
   }
   plan.n_kernel_gates = unsigned(total_gates);
   size_t off = total_gates * sizeof(HqGateDesc);
@@ -360,31 +532,25 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   size_t gate_cursor = 0;
   size_t mat_cursor = mat_base;
   for (size_t di = 0; di < drafts.size(); ++di) {
-    const Draft& d = drafts[di];
-    PassInfo pi;
-    // single gates may use shorter runs than the fuser is allowed to create
-    int L = choose_run_bits(d.bits, T, d.ids.size() > 1 ? fuse_min_run : hard_min_run);
-    if (L < 0) { plan.error = "internal: pass does not fit"; return 1; }
-    make_tile(d.bits, T, L, n, pi.header);
-    make_iter_tables(pi.header, V);
+    PassInfo& pi = infos[di];
     pi.header.n_gates = uint32_t(merged[di].size());
     pi.header.gates_off = uint32_t(gate_cursor * sizeof(HqGateDesc));
     const int Tbits = int(pi.header.tile_bits);
     const int Tu = Tbits - V;
-    for (const Cluster& cluster : merged[di]) {
+    for (size_t ci = 0; ci < merged[di].size(); ++ci) {
+      const Cluster& cluster = merged[di][ci];
+      const GateLayout& gl = layouts[di][ci];
       const Canon& c = cluster.gate;
       HqGateDesc gd;
       memset(&gd, 0, sizeof(gd));
       gd.k = c.k;
-      gd.kind = c.k <= HQ_SMALL_K ? HQ_GATE_SMALL : HQ_GATE_BIG;
+      gd.kind = gl.mma ? HQ_GATE_MMA : (c.k <= HQ_SMALL_K ? HQ_GATE_SMALL : HQ_GATE_BIG);
       gd.mat_off = uint32_t(mat_cursor);
       std::vector<bool> is_t;
       is_t.assign(size_t(Tbits), false);
       for (unsigned i = 0; i < c.k; ++i) {
-        const int lb = local_bit(pi.header, c.pos[i]);
-        if (lb < 0) { plan.error = "internal: target bit outside tile"; return 1; }
-        gd.tpos[i] = uint8_t(lb);
-        is_t[size_t(lb)] = true;
+        gd.tpos[i] = gl.tpos[i];
+        is_t[size_t(gl.tpos[i])] = true;
       }
       // canonical positions are ascending globally, hence ascending locally too
       std::vector<unsigned> free_bits;
@@ -392,32 +558,33 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         for (int u = 0; u < Tu; ++u)
           if (!is_t[size_t(u + V)]) free_bits.push_back(unsigned(u));
         free_bits = lane_order(free_bits);
-      } else {
+      } else if (gd.kind == HQ_GATE_BIG) {
         for (int a = 0; a < Tbits; ++a)
           if (!is_t[size_t(a)]) free_bits.push_back(unsigned(a));
       }
       gd.n_free = uint32_t(free_bits.size());
       for (size_t i = 0; i < free_bits.size() && i < 16; ++i) gd.q[i] = uint8_t(free_bits[i]);
       if (gd.kind == HQ_GATE_SMALL) make_lane_tables(gd, Tu, V);
+      if (gd.kind == HQ_GATE_MMA) make_mma_tables(gd, gl.L, V);
       if (gd.kind == HQ_GATE_SMALL && dtype == HQ_DTYPE_C128 && opts.fast_slots != 0 && (gd.k == 2 || gd.k == 3)) {
         make_rowpair_tables(gd, Tu);
         gd.kind = HQ_GATE_ROWPAIR;
       }
       memcpy(plan.program.data() + gate_cursor * sizeof(HqGateDesc), &gd, sizeof(gd));
-      if (dtype == HQ_DTYPE_C64)
+      if (gd.kind == HQ_GATE_MMA)
+        write_mma_fragments(plan.program, mat_cursor, c, gl.L, dtype);
+      else if (dtype == HQ_DTYPE_C64)
         write_matrix<float>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
       else
         write_matrix<double>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
-      mat_cursor += ((esz << (2 * c.k)) + 15) & ~size_t(15);
+      mat_cursor += gl.bytes;
       ++gate_cursor;
-      {
-        const size_t slot = size_t(&cluster - &merged[di][0]);
-        if (dtype == HQ_DTYPE_C64 && opts.fast_slots != 0 && slot < HQ_FAST_SLOTS && c.k == 2 && gd.tpos[0] != 0) {
-          pi.header.fast_mask |= 1u << slot;
-          for (size_t e = 0; e < 16; ++e) {
-            pi.header.fast_u[slot][2 * e] = float(c.U[e].real());
-            pi.header.fast_u[slot][2 * e + 1] = float(c.U[e].imag());
-          }
+      if (dtype == HQ_DTYPE_C64 && gd.kind == HQ_GATE_SMALL && opts.fast_slots != 0 && ci < HQ_FAST_SLOTS && c.k == 2 &&
+          gd.tpos[0] != 0) {
+        pi.header.fast_mask |= 1u << ci;
+        for (size_t e = 0; e < 16; ++e) {
+          pi.header.fast_u[ci][2 * e] = float(c.U[e].real());
+          pi.header.fast_u[ci][2 * e + 1] = float(c.U[e].imag());
         }
       }
       for (unsigned id : cluster.ids) pi.gate_ids.push_back(canon_id[id]);

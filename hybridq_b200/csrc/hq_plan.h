@@ -36,6 +36,9 @@ struct PlanOptions {
   int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (2)
   int merge_pass_cost = -1; // -1 = default (12)
   int fast_slots = 1;       // 0 = never use the constant-bank fast slots (measurements)
+  // Tensor-core path (hq_mma.cuh): gates with mma_min_k <= k <= HQ_MMA_MAX_K are applied with
+  // mma.sync (3xTF32 for complex64, FP64 for complex128).  0 = never, -1 = default for the dtype.
+  int mma_min_k = -1;
 };
 
 struct PassInfo {
@@ -59,6 +62,7 @@ struct Plan {
 int default_tile_bits(int dtype);
 int default_min_run_bits(int dtype);
 int default_merge_max_k(int dtype);
+int default_mma_min_k(int dtype);
 
 // Build a plan.  Returns 0 on success; on failure returns non-zero and sets plan.error.
 int plan_build(Plan& plan, int dtype, unsigned n_qubits, const std::vector<GateIn>& gates,

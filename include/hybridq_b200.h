@@ -130,6 +130,8 @@ typedef struct hq_plan_options {
   int merge_pass_cost;      /* cost model: cost(k) = 4*2^k + merge_pass_cost; -1 = default (12) */
   int fast_slots;           /* complex64: pass the first 8 k=2 matrices of a pass as kernel parameters
                                (constant-bank FFMA operands); 0 = off, anything else = on (default) */
+  int mma_min_k;            /* tensor-core path: gates with mma_min_k <= k <= 6 run on mma.sync (3xTF32 for
+                               complex64, FP64 for complex128); 0 = never, -1 = default (3 complex64, 2 complex128) */
 } hq_plan_options;
 
 /* gates: n_gates entries; ks[g] = number of target bits; pos_flat = concatenated positions;

@@ -41,6 +41,16 @@ def product_state(spec, ctype):
     return psi.astype(ctype)
 
 
+_EMU_DEFAULTS = (0, -1, 1, 0, 0, -1, -1, 1, -1)   # PlanOptions field order, mma_min_k last
+
+
+def _emu_opts(opts):
+    if not opts:
+        return None
+    o = tuple(opts)
+    return (ctypes.c_int * 9)(*(o + _EMU_DEFAULTS[len(o):]))
+
+
 class Emu:
     """ctypes face of libhq_emu.so (CPU model of the kernel phases + the planner)."""
 
@@ -65,14 +75,15 @@ class Emu:
         n = int(round(np.log2(psi.size)))
         ks, pos, U = self._pack(gates)
         st = np.ascontiguousarray(psi).copy()
-        o = (ctypes.c_int * 8)(*(tuple(opts) + (-1, -1, 1))[:8]) if opts else None
-        info = (ctypes.c_int * 3)()
+        o = _emu_opts(opts)
+        info = (ctypes.c_int * 4)()
         err = ctypes.create_string_buffer(256)
         rc = self.lib.hq_emu_run_circuit(dt, n, len(gates), ks.ctypes.data_as(ctypes.c_void_p),
                                          pos.ctypes.data_as(ctypes.c_void_p), U.ctypes.data_as(ctypes.c_void_p),
                                          o, st.ctypes.data_as(ctypes.c_void_p), info, err, 256)
         if rc:
             raise RuntimeError(err.value.decode())
+        self.last_info = {"n_passes": info[0], "n_gates": info[1], "n_kernel_gates": info[2], "n_mma_gates": info[3]}
         return st, info[0], info[1]
 
     def bitperm(self, psi, perm, opts=None):
@@ -80,7 +91,7 @@ class Emu:
         n = int(round(np.log2(psi.size)))
         st = np.ascontiguousarray(psi).copy()
         p = np.ascontiguousarray(perm, dtype=np.uint32)
-        o = (ctypes.c_int * 8)(*(tuple(opts) + (-1, -1, 1))[:8]) if opts else None
+        o = _emu_opts(opts)
         info = (ctypes.c_int * 3)()
         err = ctypes.create_string_buffer(256)
         rc = self.lib.hq_emu_bitperm(dt, n, p.ctypes.data_as(ctypes.c_void_p), o,
@@ -93,7 +104,7 @@ class Emu:
         """Planner only: returns list of passes {tile_bits, n_high, n_gates, has_perm, high_pos, gate_ids}."""
         ks = np.array([len(p) for p in gates_pos], dtype=np.uint32)
         pos = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint32) for p in gates_pos]))
-        o = (ctypes.c_int * 8)(*(tuple(opts) + (-1, -1, 1))[:8]) if opts else None
+        o = _emu_opts(opts)
         out = np.zeros(64 * (len(gates_pos) + 4), dtype=np.uint32)
         w = self.lib.hq_emu_plan_dump(dtype, n, len(gates_pos), ks.ctypes.data_as(ctypes.c_void_p),
                                       pos.ctypes.data_as(ctypes.c_void_p), o,

@@ -32,7 +32,8 @@ def test_random_circuits_vs_oracle(emu, oracle, c_oracle, ctype, n):
         ref = oracle.evolve_oracle(psi, [(u.astype(ctype), p) for u, p in gates], c_oracle)
         for opts in (None, (8, 2, 1, 0, 0), (8, 3, 0, 0, 0), (9, 1, 1, 4, 0), (13, 5, 1, 0, 0),
                      (9, 2, 1, 0, 0, 0, -1), (10, 2, 1, 0, 0, 2, 0), (12, 3, 1, 0, 0, 3, 30),
-                     (11, 2, 1, 0, 0, 2, -1, 0)):
+                     (11, 2, 1, 0, 0, 2, -1, 0), (12, 3, 1, 0, 0, 3, -1, 1, 2), (13, 4, 1, 0, 0, 4, -1, 1, 2),
+                     (9, 2, 1, 0, 0, 2, -1, 1, 0), (10, 2, 0, 0, 0, 0, -1, 1, 2)):
             out, n_pass, n_gates = emu.run(psi, gates, opts)
             assert n_gates == len(gates)
             assert np.abs(out - ref).max() < tol, (ctype, n, trial, opts)
@@ -52,10 +53,19 @@ def test_every_k_every_low_bit(emu, oracle, c_oracle, ctype):
             if len(set(pos)) != k:
                 continue
             U = _rand_gate(rng, n, k)[0]
+            U2 = _rand_gate(rng, n, k)[0]
             ref = oracle.evolve_oracle(psi, [(U.astype(ctype), pos)], c_oracle)
+            ref2 = oracle.evolve_oracle(ref, [(U2.astype(ctype), pos[::-1])], c_oracle)
+            tol = 2e-5 if ctype == "complex64" else 1e-12
             for T in (10, 12):
-                out, _, _ = emu.run(psi, [(U, pos)], (T, 1, 0, 0, 0))
-                assert np.abs(out - ref).max() < (2e-5 if ctype == "complex64" else 1e-12), (k, low, T)
+                out, _, _ = emu.run(psi, [(U, pos)], (T, 1, 0, 0, 0, -1, -1, 1, 0))        # FMA paths
+                assert np.abs(out - ref).max() < tol, (k, low, T)
+                assert emu.last_info["n_mma_gates"] == 0
+                # tensor-core path (k = 2..6): two unmerged gates in one pass (a lone k <= 2 gate keeps
+                # its plain matrix for the direct kernel)
+                out, n_pass, _ = emu.run(psi, [(U, pos), (U2, pos[::-1])], (T, 1, 1, 0, 0, 0, -1, 1, 2))
+                assert np.abs(out - ref2).max() < tol, (k, low, T, "mma")
+                assert n_pass == 1 and emu.last_info["n_mma_gates"] == (2 if 2 <= k <= 6 else 0), (k, low, T)
 
 
 def test_golden_circuits_through_emu(emu, golden):

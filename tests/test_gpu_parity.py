@@ -114,6 +114,33 @@ def test_device_apply_every_k_any_bits(hb, oracle, c_oracle, ctype):
 
 
 @pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_tensor_core_gates_vs_oracle(hb, oracle, c_oracle, ctype):
+    """mma.sync path (3xTF32 / FP64), k = 2..6, targets on the lowest bits (incl. amplitude bit 0, i.e.
+    inside the 16-byte unit for complex64), the highest bits and random bits; two unmerged gates per pass
+    so that k = 2 takes the tensor-core path too; full-size and small tiles."""
+    rng = np.random.default_rng(77)
+    for n in (14, 9):
+        psi = _rand_state(rng, n, ctype)
+        for k in range(2, 7):
+            for variant in range(4):
+                if variant == 0:
+                    pos = list(range(k))
+                elif variant == 1:
+                    pos = list(range(n - k, n))
+                else:
+                    pos = [int(x) for x in rng.permutation(n)[:k]]
+                pos = [int(x) for x in rng.permutation(pos)]
+                gates = [(_haar(rng, k), pos), (_haar(rng, k), pos[::-1])]
+                ref = oracle.evolve_oracle(psi, [(U.astype(ctype), p) for U, p in gates], c_oracle)
+                for T in (0, 10):
+                    plan = hb.Plan(gates, n, ctype, hb.PlanOptions(T, 1, 1, 0, 0, 0, -1, 1, 2))
+                    assert plan.n_passes == 1 and plan.n_kernel_gates == 2
+                    st = hb.DeviceState(n, ctype).upload(psi)
+                    plan.run(st)
+                    assert np.abs(st.download() - ref).max() <= TOL[ctype], (n, k, pos, T)
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
 def test_plan_variants_vs_oracle(hb, oracle, c_oracle, ctype):
     from hybridq_b200.circuits import matching_circuit, to_positions
     rng = np.random.default_rng(22)
@@ -131,7 +158,9 @@ def test_plan_variants_vs_oracle(hb, oracle, c_oracle, ctype):
             for opts in (None, hb.PlanOptions(10, 3, 1, 0, 0), hb.PlanOptions(13, 5, 1, 0, 0),
                          hb.PlanOptions(12, 5, 0, 0, 0), hb.PlanOptions(11, 1, 1, 3, 0),
                          hb.PlanOptions(12, 5, 1, 0, 0, 0, -1), hb.PlanOptions(12, 4, 1, 0, 0, 2, 0),
-                         hb.PlanOptions(13, 5, 1, 0, 0, 3, 24)):
+                         hb.PlanOptions(13, 5, 1, 0, 0, 3, 24), hb.PlanOptions(mma_min_k=2), hb.PlanOptions(mma_min_k=0),
+                         hb.PlanOptions(13, 5, 1, 0, 0, 4, -1, 1, 2), hb.PlanOptions(11, 2, 1, 0, 0, 3, -1, 1, 2),
+                         hb.PlanOptions(12, 5, 1, 0, 0, 0, -1, 1, 2)):
                 plan = hb.Plan(lowered, n, ctype, opts)
                 st = hb.DeviceState(n, ctype).upload(psi)
                 plan.run(st)

@@ -125,7 +125,7 @@ struct GateTab {
 };
 
 // MODE 0: complex64 unit path, 1: complex64 amplitude path, 2: complex128
-template <int KS, int MODE, int OCC, int SPLIT>
+template <int KS, int MODE, int OCC, int SPLIT, int UNR>
 __global__ void __launch_bounds__(256, OCC) k_gates(void* gtile, const GateTab* __restrict__ tabs, const void* __restrict__ bfr,
                                                     int n_gates, int reps, int io) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(256, OCC) k_gates(void* gtile, const GateTab* 
           for (int e = 0; e < KS * KS; ++e) breg[e] = __ldg(&bf[e * 32]);
         }
 #pragma unroll 1
-        for (uint32_t it = 0; it < n_iter; ++it) {
-          const uint32_t sb = st ^ __ldg(&g->tbl_iter[it]);
-          hq::dmma_iter_f64<KS, (KS <= 2)>(reinterpret_cast<double2*>(smem), sb, xo, bf, breg, &g->tbl_x[t]);
+        for (uint32_t it = 0; it < n_iter; it += UNR) {
+          uint32_t sb[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
+          hq::dmma_iter_f64<KS, UNR, (KS <= 2)>(reinterpret_cast<double2*>(smem), sb, xo, bf, breg, &g->tbl_x[t]);
         }
       } else {
         const float4* bf = reinterpret_cast<const float4*>(bfr) + __ldg(&g->bf_off) + lane;
@@ -167,12 +169,14 @@ __global__ void __launch_bounds__(256, OCC) k_gates(void* gtile, const GateTab* 
         }
         const uint32_t row8 = __ldg(&g->row8);
 #pragma unroll 1
-        for (uint32_t it = 0; it < n_iter; ++it) {
-          const uint32_t sb = st ^ __ldg(&g->tbl_iter[it]);
+        for (uint32_t it = 0; it < n_iter; it += UNR) {
+          uint32_t sb[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
           if (MODE == 0)
-            hq::mma_iter_f32_unit<KS, (KS <= 2), (KS >= 16), SPLIT>(tile4, sb, xo, bf, breg, &g->tbl_x[t]);
+            hq::mma_iter_f32_unit<KS, UNR, (KS <= 2), (KS >= 16), SPLIT>(tile4, sb, xo, bf, breg, &g->tbl_x[t]);
           else
-            hq::mma_iter_f32_amp<KS, (KS <= 2), (KS >= 16), SPLIT>(reinterpret_cast<float2*>(smem), sb, sb ^ row8, xo, bf, breg, &g->tbl_x[t]);
+            hq::mma_iter_f32_amp<KS, UNR, (KS <= 2), (KS >= 16), SPLIT>(reinterpret_cast<float2*>(smem), sb, row8, xo, bf, breg, &g->tbl_x[t]);
         }
       }
       __syncthreads();
@@ -320,7 +324,7 @@ static Gate random_gate(int k, const std::vector<int>& tpos, std::mt19937& rng) 
   return g;
 }
 
-template <int KS, int MODE, int OCC, int SPLIT = 0>
+template <int KS, int MODE, int OCC, int SPLIT = 0, int UNR = 1>
 static void run_gates(const char* name, const std::vector<Gate>& gates, int reps, double clock_ghz, int sms) {
   const int n_amp = MODE == 2 ? 4096 : 8192;
   std::mt19937 rng(7);
@@ -349,7 +353,7 @@ static void run_gates(const char* name, const std::vector<Gate>& gates, int reps
                                     h64[2 * i] = amp[i].real(); h64[2 * i + 1] = amp[i].imag(); }
   if (MODE != 2) for (int i = 0; i < n_amp; ++i) amp[i] = cd(h32[2 * i], h32[2 * i + 1]);
   CK(cudaMemcpy(d_tile, MODE == 2 ? (void*)h64.data() : (void*)h32.data(), 65536, cudaMemcpyHostToDevice));
-  auto kern = k_gates<KS, MODE, OCC, SPLIT>;
+  auto kern = k_gates<KS, MODE, OCC, SPLIT, UNR>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // correctness: one CTA, one repetition
@@ -516,29 +520,41 @@ int main() {
   std::mt19937 rng(11);
   {  // 3. gate loops
     auto g2 = gate_list(2, 0, 16, false, rng);
+    auto g2c = gate_list(2, 0, 16, true, rng);
+    auto g3 = gate_list(3, 0, 16, false, rng);
+    auto g4 = gate_list(4, 0, 16, false, rng);
     run_floor<3>(g2, 40, ghz, sms);
-    run_gates<1, 0, 3>("c64 unit k=2 conflict-free", g2, 40, ghz, sms);
-    run_gates<1, 0, 3, 1>("c64 unit k=2 conflict-free split1 (rna by add+mask)", g2, 40, ghz, sms);
-    run_gates<1, 0, 3, 2>("c64 unit k=2 conflict-free split2 (cvt.rna)", g2, 40, ghz, sms);
-    run_gates<4, 0, 2, 0>("c64 unit k=4 occ2", gate_list(4, 0, 16, false, rng), 10, ghz, sms);
-    run_gates<4, 0, 2, 2>("c64 unit k=4 occ2 split2", gate_list(4, 0, 16, false, rng), 10, ghz, sms);
-    run_gates<4, 2, 2>("c128 k=4 occ2", gate_list(4, 2, 16, false, rng), 10, ghz, sms);
-    run_gates<1, 0, 3>("c64 unit k=2 same-residue targets", gate_list(2, 0, 16, true, rng), 40, ghz, sms);
-    run_gates<1, 0, 2>("c64 unit k=2 conflict-free occ2", g2, 40, ghz, sms);
-    run_gates<2, 0, 3>("c64 unit k=3", gate_list(3, 0, 16, false, rng), 20, ghz, sms);
-    run_gates<4, 0, 3>("c64 unit k=4", gate_list(4, 0, 16, false, rng), 10, ghz, sms);
-    run_gates<8, 0, 2>("c64 unit k=5", gate_list(5, 0, 8, false, rng), 6, ghz, sms);
-    run_gates<16, 0, 2>("c64 unit k=6", gate_list(6, 0, 8, false, rng), 3, ghz, sms);
-    run_gates<1, 1, 3>("c64 amp k=2 (bit 0 target)", gate_list(2, 1, 16, false, rng), 40, ghz, sms);
-    run_gates<2, 1, 3>("c64 amp k=3 (bit 0 target)", gate_list(3, 1, 16, false, rng), 20, ghz, sms);
-    run_gates<4, 1, 3>("c64 amp k=4 (bit 0 target)", gate_list(4, 1, 16, false, rng), 10, ghz, sms);
-    run_gates<8, 1, 2>("c64 amp k=5 (bit 0 target)", gate_list(5, 1, 8, false, rng), 6, ghz, sms);
-    run_gates<1, 2, 3>("c128 k=2", gate_list(2, 2, 16, false, rng), 40, ghz, sms);
-    run_gates<1, 2, 3>("c128 k=2 same-residue targets", gate_list(2, 2, 16, true, rng), 40, ghz, sms);
-    run_gates<2, 2, 3>("c128 k=3", gate_list(3, 2, 16, false, rng), 20, ghz, sms);
-    run_gates<4, 2, 3>("c128 k=4", gate_list(4, 2, 16, false, rng), 10, ghz, sms);
-    run_gates<8, 2, 2>("c128 k=5", gate_list(5, 2, 8, false, rng), 4, ghz, sms);
-    run_gates<16, 2, 2>("c128 k=6", gate_list(6, 2, 8, false, rng), 2, ghz, sms);
+    run_gates<1, 0, 3, 0, 1>("c64 unit k=2 unr1", g2, 40, ghz, sms);
+    run_gates<1, 0, 3, 0, 2>("c64 unit k=2 unr2", g2, 40, ghz, sms);
+    run_gates<1, 0, 3, 0, 4>("c64 unit k=2 unr4", g2, 40, ghz, sms);
+    run_gates<1, 0, 3, 1, 4>("c64 unit k=2 unr4 split1", g2, 40, ghz, sms);
+    run_gates<1, 0, 3, 0, 4>("c64 unit k=2 unr4 same-residue targets", g2c, 40, ghz, sms);
+    run_gates<2, 0, 3, 0, 1>("c64 unit k=3 unr1", g3, 20, ghz, sms);
+    run_gates<2, 0, 3, 0, 2>("c64 unit k=3 unr2", g3, 20, ghz, sms);
+    run_gates<2, 0, 2, 0, 2>("c64 unit k=3 unr2 occ2", g3, 20, ghz, sms);
+    run_gates<4, 0, 2, 0, 1>("c64 unit k=4 unr1 occ2", g4, 10, ghz, sms);
+    run_gates<4, 0, 2, 0, 2>("c64 unit k=4 unr2 occ2", g4, 10, ghz, sms);
+    run_gates<8, 0, 2, 0, 1>("c64 unit k=5", gate_list(5, 0, 8, false, rng), 6, ghz, sms);
+    run_gates<16, 0, 2, 0, 1>("c64 unit k=6", gate_list(6, 0, 8, false, rng), 3, ghz, sms);
+    run_gates<1, 1, 3, 0, 1>("c64 amp k=2 unr1", gate_list(2, 1, 16, false, rng), 40, ghz, sms);
+    run_gates<1, 1, 3, 0, 4>("c64 amp k=2 unr4", gate_list(2, 1, 16, false, rng), 40, ghz, sms);
+    run_gates<2, 1, 3, 0, 2>("c64 amp k=3 unr2", gate_list(3, 1, 16, false, rng), 20, ghz, sms);
+    run_gates<4, 1, 2, 0, 1>("c64 amp k=4 occ2", gate_list(4, 1, 16, false, rng), 10, ghz, sms);
+    run_gates<8, 1, 2, 0, 1>("c64 amp k=5", gate_list(5, 1, 8, false, rng), 6, ghz, sms);
+    auto d2 = gate_list(2, 2, 16, false, rng);
+    auto d3 = gate_list(3, 2, 16, false, rng);
+    auto d4 = gate_list(4, 2, 16, false, rng);
+    run_gates<1, 2, 3, 0, 1>("c128 k=2 unr1", d2, 40, ghz, sms);
+    run_gates<1, 2, 3, 0, 2>("c128 k=2 unr2", d2, 40, ghz, sms);
+    run_gates<1, 2, 3, 0, 4>("c128 k=2 unr4", d2, 40, ghz, sms);
+    run_gates<1, 2, 3, 0, 4>("c128 k=2 unr4 same-residue targets", gate_list(2, 2, 16, true, rng), 40, ghz, sms);
+    run_gates<2, 2, 3, 0, 1>("c128 k=3 unr1", d3, 20, ghz, sms);
+    run_gates<2, 2, 3, 0, 2>("c128 k=3 unr2", d3, 20, ghz, sms);
+    run_gates<4, 2, 3, 0, 1>("c128 k=4 unr1 occ3", d4, 10, ghz, sms);
+    run_gates<4, 2, 2, 0, 1>("c128 k=4 unr1 occ2", d4, 10, ghz, sms);
+    run_gates<4, 2, 2, 0, 2>("c128 k=4 unr2 occ2", d4, 10, ghz, sms);
+    run_gates<8, 2, 2, 0, 1>("c128 k=5", gate_list(5, 2, 8, false, rng), 4, ghz, sms);
+    run_gates<16, 2, 2, 0, 1>("c128 k=6", gate_list(6, 2, 8, false, rng), 2, ghz, sms);
   }
   return 0;
 }
