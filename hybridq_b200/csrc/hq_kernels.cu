@@ -25,6 +25,12 @@
 #ifndef HQ_K0F_BLOCKS
 #define HQ_K0F_BLOCKS 3   // resident CTAs per SM the k <= 2 complex64 tile kernel is compiled for
 #endif
+#ifndef HQ_MMA_BREG_KS
+#define HQ_MMA_BREG_KS 4  // gates with 2^k / 4 <= this keep their B fragments in registers for the whole gate
+#endif
+#ifndef HQ_K1D_BLOCKS
+#define HQ_K1D_BLOCKS 3   // resident CTAs per SM of the k <= 3 complex128 tile kernel (measured: 134.6 vs 142.4 ms/step)
+#endif
 
 namespace hq {
 
@@ -82,9 +88,9 @@ __device__ __forceinline__ void gate_mma_rows_f32(float4* tile, const HqGateDesc
 #pragma unroll
     for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
     if (amp)
-      mma_iter_f32_amp<KS, UNR, (KS <= 2), (KS >= 16)>(reinterpret_cast<float2*>(tile), sb, row8, xo, bf, breg, xtab);
+      mma_iter_f32_amp<KS, UNR, (KS <= HQ_MMA_BREG_KS), (KS >= 16)>(reinterpret_cast<float2*>(tile), sb, row8, xo, bf, breg, xtab);
     else
-      mma_iter_f32_unit<KS, UNR, (KS <= 2), (KS >= 16)>(tile, sb, xo, bf, breg, xtab);
+      mma_iter_f32_unit<KS, UNR, (KS <= HQ_MMA_BREG_KS), (KS >= 16)>(tile, sb, xo, bf, breg, xtab);
   }
 }
 
@@ -101,8 +107,8 @@ __device__ __forceinline__ void gate_mma(float4* tile, const HqGateDesc* __restr
 #pragma unroll
   for (int s = 0; s < KS; ++s) xo[s] = __ldg(&g->tbl_x[t + 4 * s]);
   const float4* bf = reinterpret_cast<const float4*>(prog + __ldg(&g->mat_off)) + lane;
-  float4 breg[KS <= 2 ? KS * KS : 1];
-  if (KS <= 2) {
+  float4 breg[KS <= HQ_MMA_BREG_KS ? KS * KS : 1];
+  if (KS <= HQ_MMA_BREG_KS) {
 #pragma unroll
     for (int e = 0; e < KS * KS; ++e) breg[e] = __ldg(&bf[e * 32]);
   }
@@ -123,7 +129,7 @@ __device__ __forceinline__ void gate_mma_rows_f64(double2* tile, const HqGateDes
     uint32_t sb[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
-    dmma_iter_f64<KS, UNR, (KS <= 2)>(tile, sb, xo, bf, breg, xtab);
+    dmma_iter_f64<KS, UNR, (KS <= HQ_MMA_BREG_KS)>(tile, sb, xo, bf, breg, xtab);
   }
 }
 
@@ -138,8 +144,8 @@ __device__ __forceinline__ void gate_mma(double2* tile, const HqGateDesc* __rest
 #pragma unroll
   for (int s = 0; s < KS; ++s) xo[s] = __ldg(&g->tbl_x[t + 4 * s]);
   const double2* bf = reinterpret_cast<const double2*>(prog + __ldg(&g->mat_off)) + lane;
-  double2 breg[KS <= 2 ? KS * KS : 1];
-  if (KS <= 2) {
+  double2 breg[KS <= HQ_MMA_BREG_KS ? KS * KS : 1];
+  if (KS <= HQ_MMA_BREG_KS) {
 #pragma unroll
     for (int e = 0; e < KS * KS; ++e) breg[e] = __ldg(&bf[e * 32]);
   }
@@ -225,7 +231,9 @@ __device__ __forceinline__ void fast_slots(double2*, const HqGateDesc*, const Hq
                                            uint32_t, int, int) {}
 
 template <typename T, int KCLASS, int NBUF>
-__global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 && Traits<T>::V == 1) ? HQ_K0F_BLOCKS : ((KCLASS == 0 || (KCLASS == 1 && Traits<T>::V == 1)) ? 3 : 2)))
+__global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 && Traits<T>::V == 1) ? HQ_K0F_BLOCKS
+                                : ((KCLASS == 1 && Traits<T>::V == 0) ? HQ_K1D_BLOCKS
+                                   : ((KCLASS == 0 || (KCLASS == 1 && Traits<T>::V == 1)) ? 3 : 2))))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
                const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles) {
   typedef typename Traits<T>::Unit Unit;
