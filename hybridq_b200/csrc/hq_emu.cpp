@@ -207,7 +207,7 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
     }
     for (uint32_t gi = 0; gi < ph.n_gates; ++gi) {
       const HqGateDesc* g = gates + gi;
-      if (V == 1 && ph.max_k <= 2 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
+      if (V == 1 && ph.max_k <= 3 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
         for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
       } else if (g->kind == HQ_GATE_MMA) {
         emu_mma_gate(tile.data(), g, prog);

@@ -285,7 +285,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     __syncthreads();
 
     uint32_t gi0 = 0;
-    if (V == 1 && KCLASS == 0 && ph.fast_mask) {
+    if (V == 1 && KCLASS <= 1 && ph.fast_mask) {
       // unrolled slots: constant-bank matrices for the k = 2 gates, generic code for the others
       gi0 = n_gates < HQ_FAST_SLOTS ? n_gates : HQ_FAST_SLOTS;
       fast_slots<T, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);

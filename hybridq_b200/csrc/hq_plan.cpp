@@ -359,10 +359,25 @@ struct Cluster {
 int union_k(uint64_t a, uint64_t b) { return __builtin_popcountll(a | b); }
 
 // Greedy merging of an ordered gate list (all inside one tile).
+// Cost of one kernel matrix of k qubits inside a saturated pass, in microseconds at n = 30 (complex64)
+// / n = 29 (complex128), measured on B200 (profiles/r01/sweep_slope_b_breg4_k1d3.jsonl): the FMA
+// paths (constant-bank FFMA2 slots for complex64 k = 2, row pairs for complex128) and the tensor-core
+// path (3xTF32 / FP64 mma.sync).  Only the ratios matter.
+int measured_cost(int dtype, bool mma_on, int mma_min_k, int k) {
+  static const int c64_fma[5] = {0, 660, 665, 2180, 5280}, c64_mma[5] = {0, 660, 940, 1220, 2120};
+  static const int c128_fma[5] = {0, 620, 1255, 2650, 7190}, c128_mma[5] = {0, 620, 720, 1160, 2320};
+  if (k < 1) return 0;
+  if (k > 4) return 1 << 30;
+  const bool mma = mma_on && k >= mma_min_k;
+  return dtype == HQ_DTYPE_C64 ? (mma ? c64_mma[k] : c64_fma[k]) : (mma ? c128_mma[k] : c128_fma[k]);
+}
+
 std::vector<Cluster> merge_pass(const std::vector<Canon>& canon, const std::vector<unsigned>& ids, int max_k,
-                                int pass_cost) {
+                                int pass_cost, int dtype, bool mma_on, int mma_min_k) {
   std::vector<Cluster> cl;
-  auto cost = [&](int k) { return 4 * (1 << k) + pass_cost; };
+  // pass_cost >= 0: the analytic model 4 * 2^k + pass_cost (FMA per amplitude + one shared-memory round
+  // trip); pass_cost < 0: the measured table above
+  auto cost = [&](int k) { return pass_cost >= 0 ? 4 * (1 << k) + pass_cost : measured_cost(dtype, mma_on, mma_min_k, k); };
   for (unsigned id : ids) {
     const Canon& g = canon[id];
     uint64_t gm = 0;
@@ -482,13 +497,11 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   // ---- merge inside each pass, then serialise
   const int mma_min_k = opts.mma_min_k < 0 ? default_mma_min_k(dtype) : opts.mma_min_k;
   const bool mma_on = mma_min_k >= 2;
-  // Measured on B200 (profiles/r01/sweep_mma_a.jsonl, benchmark circuit): complex128 is fastest with the
-  // tensor-core path for every k >= 2 and merging up to k = 3 (a merged k = 3 DMMA matrix costs ~1.9x a
-  // k = 2 one: merge_pass_cost 2); complex64 keeps merging at k <= 2, where the constant-bank FFMA2 slots
-  // still beat 3xTF32 (127 vs 160 ms/step), and uses the tensor cores for the k >= 3 gates it is given.
-  const int merge_default = (mma_on && dtype == HQ_DTYPE_C128) ? 3 : default_merge_max_k(dtype);
+  // Merging is decided by the measured per-matrix costs (measured_cost above) unless the caller asks for
+  // the analytic model with merge_pass_cost >= 0.  Without the tensor-core path nothing above k = 2 pays.
+  const int merge_default = mma_on ? HQ_SMALL_K : default_merge_max_k(dtype);
   const int merge_max_k = opts.merge_max_k < 0 ? merge_default : std::min(opts.merge_max_k, HQ_SMALL_K);
-  const int merge_pass_cost = opts.merge_pass_cost < 0 ? ((mma_on && dtype == HQ_DTYPE_C128) ? 2 : 12) : opts.merge_pass_cost;
+  const int merge_pass_cost = opts.merge_pass_cost;
   std::vector<std::vector<Cluster>> merged(drafts.size());
   std::vector<PassInfo> infos(drafts.size());
   struct GateLayout { bool mma = false; MmaLayout L; uint8_t tpos[16] = {0}; size_t bytes = 0; };
@@ -497,7 +510,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   size_t mat_bytes = 0;
   const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
   for (size_t d = 0; d < drafts.size(); ++d) {
-    merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost);
+    merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost, dtype, mma_on, mma_min_k);
     total_gates += merged[d].size();
     // single gates may use shorter runs than the fuser is allowed to create
     const int L = choose_run_bits(drafts[d].bits, T, drafts[d].ids.size() > 1 ? fuse_min_run : hard_min_run);

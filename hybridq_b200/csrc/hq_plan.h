@@ -32,9 +32,10 @@ struct PlanOptions {
   // In-pass gate merging (the reference does this on the host too: utils.compress +
   // to_matrix_gate, /root/reference/hybridq/circuit/utils.py:467, :419, default max 4 qubits).
   // Two gates of a pass are multiplied into one matrix when that does not raise the cost
-  // cost(k) = 4 * 2^k + merge_pass_cost  (FMA per amplitude + one shared-memory round trip).
-  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (2)
-  int merge_pass_cost = -1; // -1 = default (12)
+  // cost(k) of a merged matrix: the per-matrix times measured on B200 (hq_plan.cpp, measured_cost), or,
+  // with merge_pass_cost >= 0, the analytic model 4 * 2^k + merge_pass_cost.
+  int merge_max_k = -1;     // largest merged gate; 0 = no merging; -1 = default (4 with the tensor-core path, else 2)
+  int merge_pass_cost = -1; // -1 = measured cost table
   int fast_slots = 1;       // 0 = never use the constant-bank fast slots (measurements)
   // Tensor-core path (hq_mma.cuh): gates with mma_min_k <= k <= HQ_MMA_MAX_K are applied with
   // mma.sync (3xTF32 for complex64, FP64 for complex128).  0 = never, -1 = default for the dtype.

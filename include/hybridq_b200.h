@@ -126,8 +126,9 @@ typedef struct hq_plan_options {
   int lookahead;            /* 0 = default */
   int merge_max_k;          /* in-pass merging of gates into one matrix of at most this many qubits
                                (the reference's host-side `compress`, circuit/utils.py:467);
-                               0 = off, -1 = default (2) */
-  int merge_pass_cost;      /* cost model: cost(k) = 4*2^k + merge_pass_cost; -1 = default (12) */
+                               0 = off, -1 = default (4 with the tensor-core path, else 2) */
+  int merge_pass_cost;      /* >= 0: analytic cost model cost(k) = 4*2^k + merge_pass_cost;
+                               -1 = per-matrix costs measured on B200 (default) */
   int fast_slots;           /* complex64: pass the first 8 k=2 matrices of a pass as kernel parameters
                                (constant-bank FFMA operands); 0 = off, anything else = on (default) */
   int mma_min_k;            /* tensor-core path: gates with mma_min_k <= k <= 6 run on mma.sync (3xTF32 for

@@ -62,15 +62,13 @@ for ctype, n in (("complex64", args.n64), ("complex128", args.n128)):
     gates = matching_circuit(n, depth=20, seed=n)
     lowered, _ = to_positions(gates, qubits=list(range(n)))
     variants = [("default", None),
-                ("mma off, merge 2", hb.PlanOptions(mma_min_k=0)),
-                ("mma>=2, merge 2", hb.PlanOptions(merge_max_k=2, mma_min_k=2)),
-                ("mma>=2, merge 3", hb.PlanOptions(merge_max_k=3, mma_min_k=2)),
-                ("mma>=3, merge 3", hb.PlanOptions(merge_max_k=3, mma_min_k=3)),
-                ("mma>=3, merge 3, cost 4", hb.PlanOptions(merge_max_k=3, merge_pass_cost=4, mma_min_k=3)),
-                ("mma>=3, merge 3, cost 24", hb.PlanOptions(merge_max_k=3, merge_pass_cost=24, mma_min_k=3)),
-                ("mma>=2, merge 4", hb.PlanOptions(merge_max_k=4, mma_min_k=2)),
-                ("mma>=2, merge 4, cost 30", hb.PlanOptions(merge_max_k=4, merge_pass_cost=30, mma_min_k=2)),
-                ("mma>=2, merge 3, T-1", hb.PlanOptions(tile_bits=(12 if ctype == "complex64" else 11), merge_max_k=3, mma_min_k=2))]
+                ("mma off", hb.PlanOptions(mma_min_k=0)),
+                ("merge 2 analytic (old default)", hb.PlanOptions(merge_max_k=2, merge_pass_cost=12)),
+                ("merge 3 table", hb.PlanOptions(merge_max_k=3)),
+                ("merge 4 table, mma>=2", hb.PlanOptions(mma_min_k=2)),
+                ("merge 3 analytic cost 12", hb.PlanOptions(merge_max_k=3, merge_pass_cost=12)),
+                ("merge 3 analytic cost 2", hb.PlanOptions(merge_max_k=3, merge_pass_cost=2)),
+                ("merge 4 analytic cost 30", hb.PlanOptions(merge_max_k=4, merge_pass_cost=30))]
     for label, opts in variants:
         plan = hb.Plan(lowered, n, ctype, opts)
         ms = timed(plan, st, args.reps)
