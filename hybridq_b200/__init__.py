@@ -4,6 +4,7 @@ Importing this package loads ``hybridq_b200/lib/libhybridq_b200.so`` and raises 
 missing: there is no CPU fallback.  Public surface:
 
 * :func:`simulate`            mirror of ``hybridq.circuit.simulation.simulate(optimize='evolution')``
+* :func:`expectation_value`   mirror of ``hybridq.circuit.simulation.expectation_value`` (device reduction)
 * :func:`dot`, :func:`transpose`  mirrors of ``hybridq.utils.dot`` / ``hybridq.utils.transpose``
 * :class:`DeviceState`, :class:`Plan`, :class:`PlanOptions`  device-resident state and circuit plans
 * :mod:`hybridq_b200.circuits`  seeded synthetic circuits and the ``GateApply`` gate stand-in
@@ -12,7 +13,7 @@ missing: there is no CPU fallback.  Public surface:
 """
 from ._lib import lib, PlanOptions, HybridQB200Error, DROPIN_DIR, LIBPATH  # noqa: F401
 from .state import DeviceState, Plan, BitPermPlan  # noqa: F401
-from .simulate import simulate  # noqa: F401
+from .simulate import simulate, expectation_value  # noqa: F401
 from .dot import dot, transpose, to_complex  # noqa: F401
 from . import circuits  # noqa: F401
 

@@ -93,6 +93,10 @@ _proto("hq_init_random_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, cty
 _proto("hq_norm2_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), _vp)
 _proto("hq_vdot_dev", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), _vp)
 _proto("hq_scale_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_double, _vp)
+_proto("hq_marginal_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes.c_uint,
+       ctypes.POINTER(ctypes.c_double), _vp)
+_proto("hq_project_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes.c_uint, ctypes.c_uint,
+       ctypes.c_double, ctypes.c_double, _vp)
 _proto("hq_plan_create", _vp, ctypes.c_int, ctypes.c_uint, ctypes.c_uint, _u32p, _u32p,
        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(PlanOptions))
 _proto("hq_plan_create_bitperm", _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes.POINTER(PlanOptions))
@@ -116,7 +120,7 @@ EXPORTED = [
     "hq_free", "hq_host_alloc", "hq_host_free", "hq_memcpy_h2d", "hq_memcpy_d2h", "hq_memcpy_d2d",
     "hq_stream_sync", "hq_apply_U_dev", "hq_apply_U_direct_dev", "hq_swap_dev", "hq_pack_dev",
     "hq_unpack_dev", "hq_init_product_dev", "hq_init_random_dev", "hq_norm2_dev", "hq_vdot_dev",
-    "hq_scale_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
+    "hq_scale_dev", "hq_marginal_dev", "hq_project_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
     "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_flops", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
     "hq_set_tuning", "hq_launch_count", "hq_launch_count_reset",
 ]

@@ -39,6 +39,27 @@ class GateApply:
         return all(w in ("qubits", "matrix", "n_qubits", "name", "tags") for w in what)
 
 
+@dataclass
+class ProjectionApply:
+    """Stand-in for ``hybridq.gate.Projection`` (gate/projection.py:122): project the qubits onto the z-basis
+    state ``state`` (a string of 0/1, one character per qubit) and renormalise.  Carries no ``apply``: both this
+    and the reference's ProjectionGate run on the device inside :func:`hybridq_b200.simulate`."""
+    qubits: tuple
+    state: str
+    name: str = "PROJECTION"
+    tags: dict = field(default_factory=dict)
+
+
+@dataclass
+class MeasureApply:
+    """Stand-in for ``hybridq.gate.Measure`` (gate/measure.py:122): sample an outcome of the qubits with
+    ``numpy.random.choice`` (the reference's generator, so seeding numpy reproduces its draw), project onto it
+    and renormalise."""
+    qubits: tuple
+    name: str = "MEASURE"
+    tags: dict = field(default_factory=dict)
+
+
 def haar_unitary(dim: int, rng: np.random.Generator) -> np.ndarray:
     from scipy.stats import unitary_group
     if dim == 1:

@@ -406,6 +406,33 @@ int hq_vdot_dev(const void* a, const void* b, int dtype, uint64_t n_amps, double
   if (!a || !b || !re_im_host) return fail("null pointer", 1);
   return reduce_partials(1, a, b, dtype, n_amps, re_im_host, stream);
 }
+int hq_marginal_dev(const void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
+                    double* out_host, void* stream) {
+  if (!state || !out_host || (k && !pos)) return fail("null pointer", 1);
+  if (k > HQ_MAX_K || k > n) return fail("too many measured bits", 1);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t bins = size_t(2) << k;
+  double* d_out = nullptr;
+  HQ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_out), bins * sizeof(double), s));
+  int rc = int(cudaMemsetAsync(d_out, 0, bins * sizeof(double), s));
+  if (rc == 0) rc = hq::launch_marginal(dtype, state, n, pos, k, d_out, stream);
+  if (rc == 0) {
+    ++g_launches;
+    rc = int(cudaMemcpyAsync(out_host, d_out, bins * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  if (rc == 0) rc = int(cudaStreamSynchronize(s));
+  cudaFreeAsync(d_out, s);
+  if (rc) return cuda_fail("marginal", rc);
+  return 0;
+}
+int hq_project_dev(void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
+                   unsigned int outcome, double scale_re, double scale_im, void* stream) {
+  if (!state || (k && !pos)) return fail("null pointer", 1);
+  const int rc = hq::launch_project(dtype, state, n, pos, k, outcome, scale_re, scale_im, stream);
+  if (rc) return cuda_fail("project", rc);
+  ++g_launches;
+  return 0;
+}
 int hq_scale_dev(void* state, int dtype, uint64_t n_amps, double factor, void* stream) {
   HQ_CUDA(hq::launch_scale(dtype, state, n_amps, factor, stream));
   ++g_launches;

@@ -820,4 +820,108 @@ int launch_vdot(int dtype, const void* a, const void* b, uint64_t n_amps, double
   return int(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------
+// measurement support (device-native counterparts of the reference's FunctionalGates
+// /root/reference/hybridq/gate/measure.py:25-75 and gate/projection.py:25-68)
+// ---------------------------------------------------------------------------------------
+struct BitsParams {
+  unsigned char pos[HQ_MAX_K];   // index bit of outcome bit j
+  unsigned k;
+};
+
+__device__ __forceinline__ unsigned outcome_of(unsigned long long i, const BitsParams& p) {
+  unsigned s = 0;
+  for (unsigned j = 0; j < p.k; ++j) s |= unsigned((i >> p.pos[j]) & 1ull) << j;
+  return s;
+}
+
+// out[2 s], out[2 s + 1] += sum over amplitudes with outcome s of re^2, im^2 (global double atomics;
+// `out` must be zeroed).  A thread keeps a running sum and flushes it to the CTA's shared-memory
+// histogram only when its outcome changes, the CTA flushes once at the end.
+template <typename T>
+__global__ void __launch_bounds__(256) hq_marginal_kernel(const T* __restrict__ state, unsigned long long n_amps,
+                                                          const BitsParams p, double* __restrict__ out) {
+  extern __shared__ double hist[];
+  const unsigned bins = 2u << p.k;
+  for (unsigned b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0.0;
+  __syncthreads();
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  double are = 0, aim = 0;
+  unsigned cur = 0;
+  bool have = false;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+    const unsigned s = outcome_of(i, p);
+    if (have && s != cur) {
+      atomicAdd(&hist[2 * cur], are);
+      atomicAdd(&hist[2 * cur + 1], aim);
+      are = aim = 0;
+    }
+    cur = s;
+    have = true;
+    const double re = double(state[2 * i]), im = double(state[2 * i + 1]);
+    are += re * re;
+    aim += im * im;
+  }
+  if (have) {
+    atomicAdd(&hist[2 * cur], are);
+    atomicAdd(&hist[2 * cur + 1], aim);
+  }
+  __syncthreads();
+  for (unsigned b = threadIdx.x; b < bins; b += blockDim.x)
+    if (hist[b] != 0.0) atomicAdd(&out[b], hist[b]);
+}
+
+int launch_marginal(int dtype, const void* state, unsigned n_qubits, const unsigned* pos, unsigned k, double* out_dev,
+                    void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (k > HQ_MAX_K || k > n_qubits) return int(cudaErrorInvalidValue);
+  BitsParams p;
+  memset(&p, 0, sizeof(p));
+  p.k = k;
+  for (unsigned j = 0; j < k; ++j) {
+    if (pos[j] >= n_qubits) return int(cudaErrorInvalidValue);
+    p.pos[j] = (unsigned char)pos[j];
+  }
+  const unsigned long long n = 1ull << n_qubits;
+  const size_t smem = (size_t(2) << k) * sizeof(double);
+  if (dtype == HQ_DTYPE_C64)
+    hq_marginal_kernel<float><<<grid_for(n, 256), 256, smem, s>>>((const float*)state, n, p, out_dev);
+  else
+    hq_marginal_kernel<double><<<grid_for(n, 256), 256, smem, s>>>((const double*)state, n, p, out_dev);
+  return int(cudaGetLastError());
+}
+
+// amplitudes whose outcome differs from `outcome` become 0, the others are scaled plane-wise
+template <typename T>
+__global__ void __launch_bounds__(256) hq_project_kernel(T* __restrict__ state, unsigned long long n_amps, const BitsParams p,
+                                                         unsigned outcome, T scale_re, T scale_im) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+    const bool keep = outcome_of(i, p) == outcome;
+    typename Traits<T>::Cplx v = reinterpret_cast<typename Traits<T>::Cplx*>(state)[i];
+    v.x = keep ? v.x * scale_re : T(0);
+    v.y = keep ? v.y * scale_im : T(0);
+    reinterpret_cast<typename Traits<T>::Cplx*>(state)[i] = v;
+  }
+}
+
+int launch_project(int dtype, void* state, unsigned n_qubits, const unsigned* pos, unsigned k, unsigned outcome,
+                   double scale_re, double scale_im, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (k > HQ_MAX_K || k > n_qubits || outcome >= (1u << k)) return int(cudaErrorInvalidValue);
+  BitsParams p;
+  memset(&p, 0, sizeof(p));
+  p.k = k;
+  for (unsigned j = 0; j < k; ++j) {
+    if (pos[j] >= n_qubits) return int(cudaErrorInvalidValue);
+    p.pos[j] = (unsigned char)pos[j];
+  }
+  const unsigned long long n = 1ull << n_qubits;
+  if (dtype == HQ_DTYPE_C64)
+    hq_project_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((float*)state, n, p, outcome, float(scale_re), float(scale_im));
+  else
+    hq_project_kernel<double><<<grid_for(n, 256), 256, 0, s>>>((double*)state, n, p, outcome, scale_re, scale_im);
+  return int(cudaGetLastError());
+}
+
 }  // namespace hq

@@ -53,4 +53,12 @@ int launch_norm2(int dtype, const void* state, uint64_t n_amps, double* partial,
 int launch_vdot(int dtype, const void* a, const void* b, uint64_t n_amps, double* partial,
                 unsigned n_partial, void* stream);
 
+// out_dev[2 s], out_dev[2 s + 1] += sum of re^2, im^2 over the amplitudes whose index bits pos[0..k) spell the
+// outcome s (bit j of s = index bit pos[j]); out_dev holds 2 * 2^k doubles and must be zeroed (measure.py:25-50)
+int launch_marginal(int dtype, const void* state, unsigned n_qubits, const unsigned* pos, unsigned k,
+                    double* out_dev, void* stream);
+// projection onto one outcome with plane-wise scale factors (projection.py:25-68)
+int launch_project(int dtype, void* state, unsigned n_qubits, const unsigned* pos, unsigned k, unsigned outcome,
+                   double scale_re, double scale_im, void* stream);
+
 }  // namespace hq

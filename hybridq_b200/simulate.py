@@ -58,6 +58,8 @@ def _is_functional(gate) -> bool:
     hq = _try_hybridq()
     if hq is not None and isinstance(gate, hq[2].FunctionalGate):
         return True
+    if getattr(gate, "name", None) in ("PROJECTION", "MEASURE") and not callable(getattr(gate, "matrix", None)):
+        return True
     prov = getattr(gate, "provides", None)
     if callable(prov):
         try:
@@ -71,7 +73,8 @@ def _is_functional(gate) -> bool:
 def _flatten(circuit) -> list:
     out = []
     for g in circuit:
-        if hasattr(g, "qubits") and (callable(getattr(g, "matrix", None)) or callable(getattr(g, "apply", None))):
+        if hasattr(g, "qubits") and (callable(getattr(g, "matrix", None)) or callable(getattr(g, "apply", None))
+                                     or getattr(g, "name", None) in ("PROJECTION", "MEASURE")):
             out.append(g)
         elif hasattr(g, "__iter__"):
             out.extend(_flatten(g))
@@ -163,9 +166,9 @@ def simulate(circuit,
         gates = list(circuit)
     else:
         gates = _flatten(circuit)
+        qubits = _sorted_qubits({q for g in gates for q in g.qubits})    # before identities go (simulation.py:258, :290)
         if remove_id_gates:
             gates = [g for g in gates if getattr(g, "name", None) != "I"]
-        qubits = _sorted_qubits({q for g in gates for q in g.qubits})
     n_qubits = len(qubits)
 
     # initial / final state checks (simulation.py:261-286, :415-426)
@@ -213,6 +216,8 @@ def simulate(circuit,
                 cur = []
             segments.append(("functional", g))
         elif callable(getattr(g, "matrix", None)) and hasattr(g, "qubits"):
+            if getattr(g, "name", None) == "I":
+                continue                     # kept only to pin the qubit register (remove_id_gates=False)
             U = np.asarray(g.matrix(), dtype=complex_type, order="C")
             pos = [qmap[q] for q in reversed(tuple(g.qubits))]
             cur.append((U, pos))
@@ -265,6 +270,32 @@ def simulate(circuit,
     else:
         psi = state
     return (psi, info) if kwargs["return_info"] else psi
+
+
+def expectation_value(state, op, qubits_order, complex_type: Any = "complex64", backend: Any = "numpy",
+                      verbose: bool = False, **kwargs):
+    """<state| op |state> with the evolution on the GPU: mirror of the reference's
+    ``expectation_value`` (/root/reference/hybridq/circuit/simulation/simulation.py:1125-1217): same
+    arguments, same checks, same result ``sum(simulate(op, state) * conj(state))``.  The evolved
+    state never leaves the device: the inner product is a device reduction (``hq_vdot_dev``)."""
+    kwargs["remove_id_gates"] = False
+    state = np.asarray(state)
+    n_qubits = state.ndim
+    qubits_order = list(qubits_order)
+    if len(qubits_order) != n_qubits:
+        raise ValueError("'qubits_order' must have the same number of qubits of 'state'.")
+    op = list(_flatten(op))
+    used = {q for g in op for q in g.qubits}
+    if used.difference(qubits_order):
+        raise ValueError("'op' has qubits not included in 'qubits_order'.")
+    from .circuits import GateApply
+    op = op + [GateApply(np.eye(2), (q,), name="I") for q in set(qubits_order).difference(used)]
+    kwargs.pop("return_numpy_array", None)
+    kwargs.pop("return_info", None)
+    evolved = simulate(op, initial_state=state, optimize="evolution", complex_type=complex_type, backend=backend,
+                       verbose=verbose, return_numpy_array=False, shard=False, **kwargs)
+    bra = DeviceState(n_qubits, evolved.complex_type, device=evolved.device).upload(state.reshape(-1))
+    return np.real_if_close(np.asarray(bra.vdot(evolved), dtype=evolved.complex_type))
 
 
 def _dist_if_sharded(shard):
@@ -324,11 +355,59 @@ def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwa
     return (psi, info) if kwargs["return_info"] else psi
 
 
+_PROJECTION_ATOL = 1e-6      # hybridq/gate/projection.py:31
+
+
+def _apply_projection(gate, state: DeviceState, qmap: dict, renormalize: bool = True) -> None:
+    """ProjectionGate on the device.  Follows the reference on split planes (projection.py:70-116 with
+    _Projection :25-68 on each plane): a plane whose projected norm is <= 1e-6 is zeroed as a whole, then
+    the state is renormalised by what is left."""
+    spec = tuple(gate.state)
+    if len(spec) != len(tuple(gate.qubits)):
+        raise ValueError("'state' is not consistent with 'axes'.")
+    if any(x not in ("0", "1", 0, 1) for x in spec):
+        raise ValueError("Only projections to the z-basis are supported at the moment.")
+    pos = [qmap[q] for q in gate.qubits]
+    outcome = sum(int(b) << j for j, b in enumerate(spec))
+    sums = state.marginal(pos)[outcome]
+    keep = [float(np.sqrt(x) > _PROJECTION_ATOL) for x in sums]
+    scale = 1.0
+    if renormalize:
+        norm = float(np.sqrt(sums[0] * keep[0] + sums[1] * keep[1]))
+        if norm != 0:
+            scale = 1.0 / norm
+    state.project(pos, outcome, keep[0] * scale, keep[1] * scale)
+
+
+def _apply_measure(gate, state: DeviceState, qmap: dict, renormalize: bool = True) -> int:
+    """MeasureGate on the device (measure.py:25-75): outcome probabilities by a device reduction, the draw
+    with numpy's global generator exactly as the reference does (`np.random.choice(size, p=probs)`, :52),
+    projection + renormalisation by a second kernel.  Outcome index: gate.qubits[0] is the most significant
+    digit (the reference transposes the measured axes to the front in gate.qubits order, :39-43)."""
+    qubits = tuple(gate.qubits)
+    k = len(qubits)
+    pos = [qmap[q] for q in reversed(qubits)]           # outcome bit j <-> qubits[k-1-j]
+    sums = state.marginal(pos)
+    probs = sums.sum(axis=1).astype(np.float32 if state.complex_type == np.complex64 else np.float64)
+    outcome = int(np.random.choice(2 ** k, p=probs))
+    scale = 1.0
+    if renormalize:
+        scale = 1.0 / float(np.sqrt(sums[outcome].sum()))
+    state.project(pos, outcome, scale, scale)
+    return outcome
+
+
 def _apply_functional(gate, state: DeviceState, qmap: dict) -> None:
     """FunctionalGate contract of the reference (simulation.py:525-554): the gate receives
     the state as a real array of shape (2,)+(2,)*n (re/im planes) plus the qubit order and
-    returns (new_psi, new_order).  With a device-resident state this is a D2H/H2D round
-    trip around arbitrary Python."""
+    returns (new_psi, new_order).  Projection and Measure gates (the reference's own FunctionalGates)
+    run on the device; anything else is a D2H/H2D round trip around arbitrary Python."""
+    name = getattr(gate, "name", None)
+    if name == "PROJECTION" and hasattr(gate, "state"):
+        return _apply_projection(gate, state, qmap)
+    if name == "MEASURE":
+        _apply_measure(gate, state, qmap)
+        return None
     n = state.n_qubits
     order = tuple(q for q, _ in sorted(qmap.items(), key=lambda x: x[1])[::-1])
     psi = state.download()

@@ -194,6 +194,27 @@ class DeviceState:
               "hq_vdot_dev")
         return complex(r[0], r[1])
 
+    def marginal(self, pos: Sequence[int], stream=None) -> np.ndarray:
+        """(2^k, 2) array: sum of re^2 and of im^2 over the amplitudes whose index bits ``pos`` spell the
+        outcome s (bit j of s = index bit pos[j]).  ``.sum(axis=1)`` are the measurement probabilities of
+        the reference's ``_Measure(get_probs_only=True)`` (hybridq/gate/measure.py:25-50)."""
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        out = np.zeros((2 ** len(pos), 2), dtype=np.float64)
+        check(lib.hq_marginal_dev(self.ptr, self.dtype, self.n_qubits,
+                                  pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos),
+                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _stream_handle(stream)),
+              "hq_marginal_dev")
+        return out
+
+    def project(self, pos: Sequence[int], outcome: int, scale_re: float = 1.0, scale_im: float = 1.0, stream=None):
+        """Zero every amplitude whose index bits ``pos`` do not spell ``outcome``; scale the others
+        plane-wise (hybridq/gate/projection.py:25-68)."""
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        check(lib.hq_project_dev(self.ptr, self.dtype, self.n_qubits,
+                                 pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos), int(outcome),
+                                 float(scale_re), float(scale_im), _stream_handle(stream)), "hq_project_dev")
+        return self
+
     def scale(self, factor: float, stream=None):
         check(lib.hq_scale_dev(self.ptr, self.dtype, self.n_amps, float(factor), _stream_handle(stream)),
               "hq_scale_dev")

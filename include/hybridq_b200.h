@@ -114,6 +114,17 @@ int hq_init_random_dev(void* state, int dtype, unsigned int n_qubits, uint64_t s
 int hq_norm2_dev(const void* state, int dtype, uint64_t n_amps, double* result_host, void* stream);
 int hq_vdot_dev(const void* a, const void* b, int dtype, uint64_t n_amps, double* re_im_host, void* stream);
 int hq_scale_dev(void* state, int dtype, uint64_t n_amps, double factor, void* stream);
+/* measurement support -- device-native halves of the reference's FunctionalGates, which otherwise force the
+ * state back to the host (hybridq/circuit/simulation/simulation.py:525-554):
+ * hq_marginal_dev: out_host[2 s] / out_host[2 s + 1] = sum of re^2 / im^2 over the amplitudes whose index bits
+ *   pos[0..k) spell the outcome s (bit j of s = index bit pos[j]); 2 * 2^k doubles; their pairwise sums are
+ *   the probabilities of hybridq/gate/measure.py:25-50 (_Measure, get_probs_only);
+ * hq_project_dev: amplitudes with another outcome become 0, the kept ones are scaled by scale_re / scale_im
+ *   plane-wise (hybridq/gate/projection.py:25-68 projects and renormalises the re and im planes separately). */
+int hq_marginal_dev(const void* state, int dtype, unsigned int n_qubits, const unsigned int* pos,
+                    unsigned int k, double* out_host, void* stream);
+int hq_project_dev(void* state, int dtype, unsigned int n_qubits, const unsigned int* pos, unsigned int k,
+                   unsigned int outcome, double scale_re, double scale_im, void* stream);
 
 /* ---- circuit plans: fuse a gate stream into tile passes once, run many times ---- */
 typedef struct hq_plan hq_plan;

@@ -13,6 +13,9 @@ Python face of the CPU oracle for the state-vector evolution hot path:
                   reference binds (/root/reference/hybridq/utils/dot.py:49-71,
                   transpose.py:42-58).  Used to pin the oracle and as the CPU baseline.
 * ``evolve_*``    gate-loop drivers over a list of ``(U, pos)`` gate-applies.
+* ``numpy_project`` / ``numpy_measure``  numpy restatements of the reference's Projection and
+                  Measure FunctionalGates (/root/reference/hybridq/gate/projection.py:25-116,
+                  gate/measure.py:25-122) on a flat complex state.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this module.  Parity status: PINNED (see
@@ -213,6 +216,47 @@ class RefCore:
 # ----------------------------------------------------------------------------------
 # gate-loop drivers
 # ----------------------------------------------------------------------------------
+def numpy_project(psi: np.ndarray, pos, bits, renormalize: bool = True, atol: float = 1e-6) -> np.ndarray:
+    """Projection of index bits `pos` onto the values `bits` (projection.py:70-116: the reference works on
+    the re and im planes separately -- a plane whose projected norm is <= atol is dropped -- and then
+    renormalises what is left)."""
+    idx = np.arange(psi.size)
+    keep = np.ones(psi.size, dtype=bool)
+    for p, b in zip(pos, bits):
+        keep &= ((idx >> int(p)) & 1) == int(b)
+    re = np.where(keep, psi.real, 0)
+    im = np.where(keep, psi.imag, 0)
+    if not np.linalg.norm(re) > atol:
+        re = np.zeros_like(re)
+    if not np.linalg.norm(im) > atol:
+        im = np.zeros_like(im)
+    out = (re + 1j * im).astype(psi.dtype)
+    if renormalize:
+        norm = np.linalg.norm(out)
+        if norm != 0:
+            out = (out / norm).astype(psi.dtype)
+    return out
+
+
+def numpy_measure(psi: np.ndarray, pos_msb_first, renormalize: bool = True):
+    """Measure (measure.py:25-75): probabilities of the outcomes of index bits `pos_msb_first` (first = most
+    significant digit of the outcome), one draw from numpy's global generator, projection, renormalisation.
+    Returns (new state, outcome)."""
+    idx = np.arange(psi.size)
+    k = len(pos_msb_first)
+    outcome_of = np.zeros(psi.size, dtype=np.int64)
+    for j, p in enumerate(pos_msb_first):
+        outcome_of |= ((idx >> int(p)) & 1) << (k - 1 - j)
+    probs = np.bincount(outcome_of, weights=(psi.real.astype(np.float64) ** 2 + psi.imag.astype(np.float64) ** 2),
+                        minlength=2 ** k)
+    probs = probs.astype(np.float32 if psi.dtype == np.complex64 else np.float64)
+    s = int(np.random.choice(2 ** k, p=probs))
+    out = np.where(outcome_of == s, psi, 0).astype(psi.dtype)
+    if renormalize:
+        out = (out / np.linalg.norm(out)).astype(psi.dtype)
+    return out, s
+
+
 def evolve_oracle(psi0: np.ndarray, gates, oracle: COracle | None = None) -> np.ndarray:
     """Apply `gates` = [(U, pos), ...] to complex psi0 (flat) with the C oracle."""
     oracle = oracle or COracle()

@@ -18,6 +18,9 @@ oracle or CUDA path):
                  string and array initial states, tuple qubit labels.
   dot.npz        `hybridq.utils.dot` through the C++ core (dot.py:139, raise_if_hcore_fails).
   transpose.npz  `hybridq.utils.transpose` through the C++ core (transpose.py:61).
+  functional.npz   `simulate(optimize='evolution')` on circuits with Projection and Measure FunctionalGates
+                 (simulation.py:525-554, gate/projection.py, gate/measure.py), numpy's generator seeded.
+  expectation.npz  `hybridq.circuit.simulation.expectation_value` (simulation.py:1125) on 12-qubit states.
   dm.npz         `hybridq.dm.circuit.simulation.simulate` (dm/circuit/simulation.py:118) on a
                  6-qubit circuit with depolarizing noise; the lowered 12-"qubit" circuit that
                  it hands to `simulate` is captured and stored as (matrix, qubit-index) lists.
@@ -313,9 +316,98 @@ def make_dm15():
           f"{np.bincount([len(g.qubits) for g in lowered])}")
 
 
+def make_functional():
+    """FunctionalGates inside `simulate(optimize='evolution')` (simulation.py:525-554): Projection
+    (gate/projection.py) and Measure (gate/measure.py; the draw uses numpy's global generator, seeded here)."""
+    from hybridq.gate import MatrixGate, Projection, Measure
+    from hybridq.circuit import Circuit
+    from hybridq.circuit.simulation import simulate
+    rng = np.random.default_rng(55)
+    out = {}
+    idx = 0
+    n = 12
+    for ctype in ("complex64", "complex128"):
+        for seed in (123, 7):
+            items = []
+            def rand_gates(m):
+                for _ in range(m):
+                    k = int(rng.integers(1, 4))
+                    items.append(("U", haar_unitary(2 ** k, rng), [int(i) for i in rng.permutation(n)[:k]]))
+            rand_gates(10)
+            items.append(("P", "10", [3, 7]))
+            rand_gates(10)
+            items.append(("M", None, [1, 5, 9]))
+            rand_gates(6)
+            items.append(("M", None, [0]))
+            rand_gates(4)
+            circ = Circuit(MatrixGate(U, qubits=q) if kind == "U" else
+                           (Projection(state=U, qubits=q) if kind == "P" else Measure(qubits=q))
+                           for kind, U, q in items)
+            np.random.seed(seed)
+            psi = simulate(circ, initial_state="+" * n, optimize="evolution", simplify=False, compress=0,
+                           complex_type=ctype)
+            out[f"f{idx}_ctype"] = np.array(ctype)
+            out[f"f{idx}_seed"] = np.int32(seed)
+            out[f"f{idx}_nitems"] = np.int32(len(items))
+            for j, (kind, U, q) in enumerate(items):
+                out[f"f{idx}_i{j}_kind"] = np.array(kind)
+                out[f"f{idx}_i{j}_q"] = np.array(q, dtype=np.int32)
+                if kind == "U":
+                    out[f"f{idx}_i{j}_U"] = np.asarray(U)
+                elif kind == "P":
+                    out[f"f{idx}_i{j}_state"] = np.array(U)
+            out[f"f{idx}_out"] = np.asarray(psi).reshape(-1)
+            idx += 1
+    out["n_cases"] = np.int32(idx)
+    out["n_qubits"] = np.int32(n)
+    np.savez_compressed(HERE / "functional.npz", **out)
+    print("functional.npz:", idx, "cases; norms", [float(np.linalg.norm(out[f"f{i}_out"])) for i in range(idx)])
+
+
+def make_expectation():
+    """`hybridq.circuit.simulation.expectation_value` (simulation.py:1125-1217): <state| op |state> with
+    op acting on a subset of the qubits (the reference pads it with identity gates)."""
+    from hybridq.gate import MatrixGate
+    from hybridq.circuit import Circuit
+    from hybridq.circuit.simulation import expectation_value
+    rng = np.random.default_rng(91)
+    out = {}
+    idx = 0
+    n = 12
+    qubits = list(range(n))
+    for ctype in ("complex64", "complex128"):
+        for n_gates, kmax in ((3, 2), (12, 3)):
+            state = rand_state(rng, n, ctype).reshape((2,) * n)
+            gl = []
+            for _ in range(n_gates):
+                k = int(rng.integers(1, kmax + 1))
+                qs = [int(i) for i in rng.permutation(n - 2)[:k]]          # qubits n-2, n-1 stay untouched
+                gl.append(MatrixGate(haar_unitary(2 ** k, rng), qubits=qs))
+            val = expectation_value(state=state, op=Circuit(gl), qubits_order=qubits, complex_type=ctype,
+                                    simplify=False, compress=0)
+            out[f"e{idx}_ctype"] = np.array(ctype)
+            out[f"e{idx}_state"] = state.reshape(-1)
+            out[f"e{idx}_ngates"] = np.int32(len(gl))
+            for j, g in enumerate(gl):
+                out[f"e{idx}_g{j}_U"] = np.asarray(g.matrix())
+                out[f"e{idx}_g{j}_q"] = np.array(g.qubits, dtype=np.int32)
+            out[f"e{idx}_value"] = np.complex128(val)
+            idx += 1
+    out["n_cases"] = np.int32(idx)
+    out["n_qubits"] = np.int32(n)
+    np.savez_compressed(HERE / "expectation.npz", **out)
+    print("expectation.npz:", idx, "cases", [complex(out[f"e{i}_value"]) for i in range(idx)])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dm15":
         make_dm15()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "expectation":
+        make_expectation()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "functional":
+        make_functional()
         sys.exit(0)
     make_apply_u()
     make_swap()
@@ -323,5 +415,7 @@ if __name__ == "__main__":
     make_dot_transpose()
     make_dm()
     make_dm15()
+    make_expectation()
+    make_functional()
     for f in sorted(HERE.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size / 1e6:.2f} MB")

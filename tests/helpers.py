@@ -25,6 +25,17 @@ def lower(gates_q, n):
     return [(U, [n - 1 - int(x) for x in reversed(q)]) for U, q in gates_q]
 
 
+def functional_items(z, i):
+    """Items of a stored circuit with FunctionalGates: ('U', matrix, qubits) | ('P', '01..', qubits) | ('M', None, qubits)."""
+    items = []
+    for j in range(int(z[f"f{i}_nitems"])):
+        kind = str(z[f"f{i}_i{j}_kind"])
+        q = [int(x) for x in z[f"f{i}_i{j}_q"]]
+        payload = z[f"f{i}_i{j}_U"] if kind == "U" else (str(z[f"f{i}_i{j}_state"]) if kind == "P" else None)
+        items.append((kind, payload, q))
+    return items
+
+
 def initial_from(z, key, n, ctype):
     init = z[key]
     if init.dtype.kind in "US":

@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from helpers import TOL, golden_gates, lower, initial_from, product_state
+from helpers import TOL, golden_gates, lower, initial_from, product_state, functional_items
 
 pytestmark = pytest.mark.gpu
 
@@ -184,6 +184,46 @@ def test_simulate_golden(hb, golden):
         assert out.shape == (2,) * n and out.dtype == np.dtype(ctype)
         assert np.abs(out.reshape(-1) - z[f"s{i}_out"]).max() <= 4 * TOL[ctype], (i, str(z[f"s{i}_tag"]))
         assert info["n_passes"] < info["n_gate_applies"]
+
+
+def test_functional_gates_golden(hb, golden):
+    """Projection and Measure run on the device inside simulate() (no D2H/H2D round trip) and reproduce the
+    reference's results, draw included (numpy's generator seeded as in the golden run)."""
+    from hybridq_b200.circuits import GateApply, ProjectionApply, MeasureApply
+    z = golden["functional"]
+    n = int(z["n_qubits"])
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"f{i}_ctype"])
+        circ = [GateApply(p, tuple(q)) if kind == "U" else (ProjectionApply(tuple(q), p) if kind == "P" else MeasureApply(tuple(q)))
+                for kind, p, q in functional_items(z, i)]
+        np.random.seed(int(z[f"f{i}_seed"]))
+        launches0 = hb.lib.hq_launch_count()
+        out = hb.simulate(circ, initial_state="+" * n, complex_type=ctype)
+        assert np.abs(out.reshape(-1) - z[f"f{i}_out"]).max() <= 4 * TOL[ctype], i
+        assert hb.lib.hq_launch_count() > launches0
+    # the marginal of a product state
+    st = hb.DeviceState(n, "complex128").init_product("+" * (n - 2) + "01")
+    m = st.marginal([0, 1, 5]).sum(axis=1)                  # bit 0 = 1, bit 1 = 0, bit 5 = +
+    want = np.zeros(8)
+    want[0b001] = want[0b101] = 0.5
+    assert np.abs(m - want).max() < 1e-12
+
+
+def test_expectation_value_golden(hb, golden):
+    """hybridq_b200.expectation_value against the reference's own expectation_value results."""
+    from hybridq_b200.circuits import GateApply
+    z = golden["expectation"]
+    n = int(z["n_qubits"])
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"e{i}_ctype"])
+        op = [GateApply(z[f"e{i}_g{j}_U"], tuple(int(x) for x in z[f"e{i}_g{j}_q"])) for j in range(int(z[f"e{i}_ngates"]))]
+        state = z[f"e{i}_state"].astype(ctype).reshape((2,) * n)
+        val = hb.expectation_value(state=state, op=op, qubits_order=list(range(n)), complex_type=ctype)
+        assert abs(complex(val) - complex(z[f"e{i}_value"])) <= (2e-6 if ctype == "complex64" else 1e-12), i
+    with pytest.raises(ValueError):
+        hb.expectation_value(state=state, op=op, qubits_order=list(range(n - 1)), complex_type=ctype)
+    with pytest.raises(ValueError):
+        hb.expectation_value(state=state, op=[GateApply(np.eye(2), (99,))], qubits_order=list(range(n)))
 
 
 def test_dm_golden(hb, golden):

@@ -4,7 +4,7 @@ present, against the reference's own compiled core."""
 import numpy as np
 import pytest
 
-from helpers import TOL, golden_gates, lower, initial_from, product_state
+from helpers import TOL, golden_gates, lower, initial_from, product_state, functional_items
 
 
 def _tol(ctype, k=1):
@@ -47,6 +47,37 @@ def test_simulate_golden(oracle, c_oracle, golden):
         out = oracle.evolve_oracle(psi0, [(U.astype(ctype), p) for U, p in gates], c_oracle)
         # compress=4 cases merge matrices before applying them: same state up to rounding
         assert np.abs(out - z[f"s{i}_out"]).max() < 4 * TOL[ctype], (i, str(z[f"s{i}_tag"]))
+
+
+def test_expectation_golden(oracle, c_oracle, golden):
+    """<state| op |state> of the reference's expectation_value (simulation.py:1125-1217)."""
+    z = golden["expectation"]
+    n = int(z["n_qubits"])
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"e{i}_ctype"])
+        gates = [(z[f"e{i}_g{j}_U"], z[f"e{i}_g{j}_q"]) for j in range(int(z[f"e{i}_ngates"]))]
+        state = z[f"e{i}_state"].astype(ctype)
+        out = oracle.evolve_oracle(state, [(U.astype(ctype), p) for U, p in lower(gates, n)], c_oracle)
+        val = complex(np.real_if_close(np.vdot(state, out)))     # as the reference returns it (:1217)
+        assert abs(val - complex(z[f"e{i}_value"])) <= (2e-6 if ctype == "complex64" else 1e-12)
+
+
+def test_functional_golden(oracle, c_oracle, golden):
+    """Projection / Measure restatements against the reference's simulate() with FunctionalGates."""
+    z = golden["functional"]
+    n = int(z["n_qubits"])
+    for i in range(int(z["n_cases"])):
+        ctype = str(z[f"f{i}_ctype"])
+        psi = product_state("+" * n, ctype)
+        np.random.seed(int(z[f"f{i}_seed"]))
+        for kind, payload, q in functional_items(z, i):
+            if kind == "U":
+                psi = oracle.evolve_oracle(psi, [(payload.astype(ctype), [n - 1 - x for x in reversed(q)])], c_oracle)
+            elif kind == "P":
+                psi = oracle.numpy_project(psi, [n - 1 - x for x in q], [int(c) for c in payload])
+            else:
+                psi, _ = oracle.numpy_measure(psi, [n - 1 - x for x in q])
+        assert np.abs(psi - z[f"f{i}_out"]).max() < 4 * TOL[ctype], i
 
 
 def test_dot_golden(oracle, golden):
