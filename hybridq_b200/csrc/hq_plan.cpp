@@ -21,6 +21,7 @@ namespace {
 const int kMaxGatesPerPass = 48;   // gate-applies per pass before merging
 
 int vbits(int dtype) { return dtype == HQ_DTYPE_C64 ? 1 : 0; }
+bool vectors_independent(const std::vector<uint32_t>& v);
 int max_tile_bits(int dtype) { return HQ_MAX_UNIT_BITS + vbits(dtype); }
 
 // Largest run length L in [Lmin, T] such that the members of `bits` at or above L fit in the
@@ -149,14 +150,14 @@ bool mma_layout(const uint8_t* tpos, int k, int Tbits, int V, MmaLayout& L) {
   const int bits = L.amp ? Tbits : Tbits - V;          // index bits of the granularity in use
   std::vector<int> tb(size_t(k), 0);                   // target bits at that granularity
   for (int i = 0; i < k; ++i) tb[size_t(i)] = L.amp ? int(tpos[i]) : int(tpos[i]) - V;
-  auto res = [&](int b) { return ((L.amp ? b - 1 : b) % 3 + 3) % 3; };   // residue of the unit bit
+  auto vec = [&](int b) { return swz_vec(L.amp ? b - 1 : b); };          // bank vector of the bit's unit bit
   // lane bits
   int c0 = 0, c1 = 1;
   if (!L.amp) {
     bool found = false;
     for (int i = 0; i < k && !found; ++i)
       for (int j = i + 1; j < k && !found; ++j)
-        if (res(tb[size_t(i)]) != res(tb[size_t(j)])) { c0 = i; c1 = j; found = true; }
+        if (vec(tb[size_t(i)]) != vec(tb[size_t(j)])) { c0 = i; c1 = j; found = true; }
   }
   int nf = 0;
   L.forder[nf++] = c0;
@@ -171,18 +172,21 @@ bool mma_layout(const uint8_t* tpos, int k, int Tbits, int V, MmaLayout& L) {
     if (!is_t[size_t(b)]) freeb.push_back(unsigned(b));
   L.row_lane_bits = L.amp ? 4 : 3;
   if (int(freeb.size()) < L.row_lane_bits) return false;
-  std::vector<int> avoid;
-  if (L.amp) avoid.push_back(res(tb[size_t(c1)]));
-  else { avoid.push_back(res(tb[size_t(c0)])); avoid.push_back(res(tb[size_t(c1)])); }
+  // unit path: a quarter-warp spans (t0, t1, g0); amplitude path: a half-warp of 8-byte accesses spans
+  // (t0 = the half of the unit, t1, g0, g1) -- the unit-level lane bits must have independent vectors
+  std::vector<uint32_t> vecs;
+  if (L.amp) vecs.push_back(vec(tb[size_t(c1)]));
+  else { vecs.push_back(vec(tb[size_t(c0)])); vecs.push_back(vec(tb[size_t(c1)])); }
   const int want = L.amp ? 2 : 1;
   for (int c = 0; c < want; ++c)
     for (size_t i = size_t(c); i < freeb.size(); ++i) {
-      const int r = res(int(freeb[i]));
-      if (std::find(avoid.begin(), avoid.end(), r) == avoid.end()) {
+      std::vector<uint32_t> trial = vecs;
+      trial.push_back(vec(int(freeb[i])));
+      if (vectors_independent(trial)) {
         const unsigned b = freeb[i];
         freeb.erase(freeb.begin() + long(i));
         freeb.insert(freeb.begin() + c, b);
-        avoid.push_back(r);
+        vecs.swap(trial);
         break;
       }
     }
@@ -274,16 +278,28 @@ int local_bit(const HqPassHeader& ph, unsigned global_bit) {
   return -1;
 }
 
-// Order the free bits so that the three lowest work-item bits land on bits with distinct
-// residues mod 3 (conflict-free quarter-warps under swz), lowest bits first otherwise.
+// true when the 3-bit bank vectors in `v` (see swz_vec) are linearly independent over GF(2)
+bool vectors_independent(const std::vector<uint32_t>& v) {
+  for (size_t m = 1; m < (size_t(1) << v.size()); ++m) {
+    uint32_t x = 0;
+    for (size_t i = 0; i < v.size(); ++i)
+      if ((m >> i) & 1u) x ^= v[i];
+    if (x == 0) return false;
+  }
+  return true;
+}
+
+// Order the free unit bits so that the three lowest work-item bits land on bits with linearly
+// independent bank vectors (conflict-free quarter-warps under swz), lowest bits first otherwise.
 std::vector<unsigned> lane_order(const std::vector<unsigned>& free_sorted) {
   std::vector<unsigned> first;
-  bool used_res[3] = {false, false, false};
+  std::vector<uint32_t> vecs;
   std::vector<bool> taken(free_sorted.size(), false);
   for (size_t i = 0; i < free_sorted.size() && first.size() < 3; ++i) {
-    const unsigned r = free_sorted[i] % 3;
-    if (!used_res[r]) {
-      used_res[r] = true;
+    std::vector<uint32_t> trial = vecs;
+    trial.push_back(swz_vec(int(free_sorted[i])));
+    if (vectors_independent(trial)) {
+      vecs.swap(trial);
       taken[i] = true;
       first.push_back(free_sorted[i]);
     }

@@ -12,11 +12,19 @@
 // tile from registers, and writes the tile back once.
 //
 // Shared-memory layout: the tile is an array of 16-byte units indexed by the local unit
-// index u; unit u lives at physical slot swz(u).  swz XOR-folds unit bits 3-5, 6-8 and 9-11
-// onto bits 0-2, which is GF(2)-linear (swz(a ^ b) = swz(a) ^ swz(b)), keeps 8 consecutive
-// units in 8 distinct 16-byte bank groups (conflict-free fills and drains), and makes a
-// quarter-warp of LDS.128 conflict-free whenever the three lowest work-item bits are mapped
-// (by HqGateDesc::q, chosen on the host) to unit bits with distinct residues mod 3.
+// index u; unit u lives at physical slot swz(u) = u ^ f(u >> 3), where f is a GF(2)-linear map of
+// unit bits 3..11 onto slot bits 0..2 (so swz(a ^ b) = swz(a) ^ swz(b) and table entries compose
+// by XOR).  Every unit bit b therefore has a 3-bit "bank vector" swz_vec(b) -- 1, 2, 4 for bits
+// 0..2 -- and a quarter-warp of 16-byte accesses whose lanes differ in three unit bits is
+// conflict-free exactly when the three vectors are linearly independent.  The vectors are
+//   bit      0 1 2 3 4 5 6 7 8 9 10 11
+//   vector   1 2 4 3 6 5 7 1 2 4  3  6
+// i.e. all seven non-zero vectors are used and only 5 of the 66 bit pairs share one (the earlier
+// u ^ (u>>3 & 7) ^ (u>>6 & 7) ^ (u>>9 & 7) used three vectors, 18 colliding pairs, which cost the
+// tensor-core k = 2 gates a 2-way conflict on 27 % of the target pairs: ncu, profiles/r01).
+// Fills and drains touch 8 consecutive units per quarter-warp (vectors 1, 2, 4): conflict-free;
+// gate work items are mapped to lanes by the host (HqGateDesc::q, mma_layout) so that the
+// lane bits of a quarter-warp land on independent vectors whenever the gate's bits allow it.
 #pragma once
 #include "hq_common.h"
 
@@ -56,8 +64,30 @@ template <> struct Traits<double> {
   static const int V = 0;
 };
 
+// bank vector of unit bit b (b < 12)
+HQ_HD uint32_t swz_vec(int b) {
+  // 3 bits per unit bit, bit 0 first: 1 2 4 3 6 5 7 1 2 4 3 6
+  const uint64_t packed = 01ull | (02ull << 3) | (04ull << 6) | (03ull << 9) | (06ull << 12) | (05ull << 15) |
+                          (07ull << 18) | (01ull << 21) | (02ull << 24) | (04ull << 27) | (03ull << 30) | (06ull << 33);
+  return uint32_t(packed >> (3 * b)) & 7u;
+}
+
+// f restricted to one 3-bit group of unit bits (first = 3, 6 or 9), as an 8-entry table packed in 24 bits
+HQ_HD uint32_t swz_group_table(int first) {
+  uint32_t t = 0;
+  for (uint32_t g = 0; g < 8; ++g) {
+    uint32_t v = 0;
+    for (int i = 0; i < 3; ++i)
+      if ((g >> i) & 1u) v ^= swz_vec(first + i);
+    t |= v << (3 * g);
+  }
+  return t;
+}
+
 HQ_HD uint32_t swz(uint32_t u) {
-  return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u) ^ ((u >> 9) & 7u);
+  const uint32_t t1 = swz_group_table(3), t2 = swz_group_table(6), t3 = swz_group_table(9);   // folded to constants
+  return u ^ ((t1 >> (3 * ((u >> 3) & 7u))) & 7u) ^ ((t2 >> (3 * ((u >> 6) & 7u))) & 7u) ^
+         ((t3 >> (3 * ((u >> 9) & 7u))) & 7u);
 }
 
 // Open a zero gap at every position of `pos` (ascending, final coordinates).
