@@ -234,6 +234,12 @@ class CudaEngine:
     def scale(self, st, f):
         st.scale(f)
 
+    def marginal(self, st, pos):
+        return st.marginal(pos)
+
+    def project(self, st, pos, outcome, scale_re, scale_im):
+        st.project(pos, outcome, scale_re, scale_im)
+
     def sync(self):
         import torch
         torch.cuda.synchronize()
@@ -260,6 +266,58 @@ class ShardedRunner:
         self.local_passes = 0
         self.exchange_ms = 0.0
         self._count_passes = True
+        self._segment = 0
+        self.complex_type = self.ctype
+
+    def replan(self, lowered: Sequence, restore: bool = True):
+        """Swap in the schedule of another gate list (the next segment of a circuit that is interrupted by
+        measurement gates); the shard buffers and their contents stay."""
+        self.ops, stats, self.final_where = plan_sharded(lowered, self.n, self.g, restore=restore)
+        for k, v in stats.items():
+            self.stats[k] = self.stats.get(k, 0) + v
+        self.n_gates += len(lowered)
+        self._segment += 1
+
+    # -- measurement support on the sharded state (canonical bit order required: call between segments) ------
+    def marginal(self, pos: Sequence[int]):
+        """(2^k, 2) sums of re^2 / im^2 per outcome of the LOGICAL index bits `pos` (bit j of the outcome =
+        index bit pos[j]), over the whole state: local reduction per rank, the rank bits contribute this rank's
+        own bit values, one all-reduce."""
+        import torch
+        if any(w != i for i, w in enumerate(self.final_where)):
+            raise RuntimeError("marginal() needs the canonical bit order (plan with restore=True)")
+        nl = self.n_local
+        local = [(j, p) for j, p in enumerate(pos) if p < nl]
+        loc = np.asarray(self.engine.marginal(self.a, [p for _, p in local]), dtype=np.float64)
+        fixed = sum((((self.rank >> (p - nl)) & 1) << j) for j, p in enumerate(pos) if p >= nl)
+        full = np.zeros((2 ** len(pos), 2), dtype=np.float64)
+        for s_loc in range(2 ** len(local)):
+            s = fixed
+            for i, (j, _) in enumerate(local):
+                s |= ((s_loc >> i) & 1) << j
+            full[s] += loc[s_loc]
+        t = torch.from_numpy(full).to(self.engine.tensor(self.a).device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def project(self, pos: Sequence[int], outcome: int, scale_re: float = 1.0, scale_im: float = 1.0):
+        """Keep the amplitudes whose LOGICAL index bits `pos` spell `outcome` (scaled plane-wise), zero the rest;
+        a rank whose own bits contradict the outcome zeroes its whole shard."""
+        nl = self.n_local
+        for j, p in enumerate(pos):
+            if p >= nl and ((self.rank >> (p - nl)) & 1) != ((outcome >> j) & 1):
+                self.engine.project(self.a, [], 0, 0.0, 0.0)
+                return self
+        local = [(j, p) for j, p in enumerate(pos) if p < nl]
+        out_loc = sum((((outcome >> j) & 1) << i) for i, (j, _) in enumerate(local))
+        self.engine.project(self.a, [p for _, p in local], out_loc, scale_re, scale_im)
+        return self
+
+    def broadcast_int(self, value: int, src: int = 0) -> int:
+        import torch
+        t = torch.tensor([int(value)], dtype=torch.int64, device=self.engine.tensor(self.a).device)
+        self.dist.broadcast(t, src)
+        return int(t.item())
 
     def describe(self):
         s = self.stats
@@ -308,9 +366,9 @@ class ShardedRunner:
         passes = 0
         for i, op in enumerate(self.ops):
             if op.kind == "local":
-                passes += self.engine.run_gates(self.a, ("g", i), op.gates)
+                passes += self.engine.run_gates(self.a, ("g", self._segment, i), op.gates)
             elif op.kind == "permute":
-                passes += self.engine.permute(self.a, ("p", i), op.perm)
+                passes += self.engine.permute(self.a, ("p", self._segment, i), op.perm)
             else:
                 if time_exchange:
                     self.engine.sync()
@@ -333,9 +391,9 @@ class ShardedRunner:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 if op.kind == "local":
-                    self.engine.run_gates(self.a, ("g", i), op.gates)
+                    self.engine.run_gates(self.a, ("g", self._segment, i), op.gates)
                 else:
-                    self.engine.permute(self.a, ("p", i), op.perm)
+                    self.engine.permute(self.a, ("p", self._segment, i), op.perm)
                 e1.record()
                 torch.cuda.synchronize()
                 total += e0.elapsed_time(e1)

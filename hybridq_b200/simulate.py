@@ -229,6 +229,7 @@ def simulate(circuit,
 
     dist = _dist_if_sharded(kwargs["shard"])
     if dist is not None:
+        kwargs["_qmap"] = qmap
         return _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwargs, t_pre)
 
     t_plan = time.perf_counter()
@@ -319,11 +320,13 @@ def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwa
     (amplitudes [rank * 2^(n-g), (rank+1) * 2^(n-g)) in canonical order).  The reference has no
     counterpart (simulation.py:379-380)."""
     from .dist import ShardedRunner
-    if any(kind != "gates" for kind, _ in segments):
-        raise NotImplementedError("FunctionalGates are not supported on a sharded state")
-    lowered = [gp for _, payload in segments for gp in payload]
+    for kind, payload in segments:
+        if kind != "gates" and getattr(payload, "name", None) not in ("PROJECTION", "MEASURE"):
+            raise NotImplementedError("only Projection and Measure FunctionalGates are supported on a sharded state")
+    qmap = kwargs.pop("_qmap")
     t_plan = time.perf_counter()
-    runner = ShardedRunner(n_qubits, lowered, complex_type, dist, plan_options=kwargs["plan_options"])
+    first = segments[0][1] if segments and segments[0][0] == "gates" else []
+    runner = ShardedRunner(n_qubits, first, complex_type, dist, plan_options=kwargs["plan_options"])
     t_plan = time.perf_counter() - t_plan
     nl = runner.n_local
     t_up = time.perf_counter()
@@ -340,7 +343,15 @@ def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwa
     t_up = time.perf_counter() - t_up
     dist.barrier()
     t0 = time.perf_counter()
-    runner.step()
+    for si, (kind, payload) in enumerate(segments):
+        if kind == "gates":
+            if si > 0:
+                runner.replan(payload)
+            runner.step()
+        elif payload.name == "PROJECTION":
+            _apply_projection(payload, runner, qmap)
+        else:
+            _apply_measure(payload, runner, qmap)
     runner.engine.sync()
     dist.barrier()
     runtime = time.perf_counter() - t0
@@ -389,7 +400,10 @@ def _apply_measure(gate, state: DeviceState, qmap: dict, renormalize: bool = Tru
     pos = [qmap[q] for q in reversed(qubits)]           # outcome bit j <-> qubits[k-1-j]
     sums = state.marginal(pos)
     probs = sums.sum(axis=1).astype(np.float32 if state.complex_type == np.complex64 else np.float64)
-    outcome = int(np.random.choice(2 ** k, p=probs))
+    if hasattr(state, "broadcast_int"):                 # sharded state: rank 0 draws for everybody
+        outcome = state.broadcast_int(int(np.random.choice(2 ** k, p=probs)) if state.rank == 0 else 0)
+    else:
+        outcome = int(np.random.choice(2 ** k, p=probs))
     scale = 1.0
     if renormalize:
         scale = 1.0 / float(np.sqrt(sums[outcome].sum()))

@@ -41,6 +41,25 @@ class OracleEngine:
     def norm2(self, st):
         return float((st.abs() ** 2).sum())
 
+    def marginal(self, st, pos):
+        psi = st.numpy()
+        idx = np.arange(psi.size)
+        s = np.zeros(psi.size, dtype=np.int64)
+        for j, p in enumerate(pos):
+            s |= ((idx >> int(p)) & 1) << j
+        out = np.zeros((2 ** len(pos), 2))
+        out[:, 0] = np.bincount(s, weights=psi.real.astype(np.float64) ** 2, minlength=2 ** len(pos))
+        out[:, 1] = np.bincount(s, weights=psi.imag.astype(np.float64) ** 2, minlength=2 ** len(pos))
+        return out
+
+    def project(self, st, pos, outcome, scale_re, scale_im):
+        psi = st.numpy()
+        idx = np.arange(psi.size)
+        keep = np.ones(psi.size, dtype=bool)
+        for j, p in enumerate(pos):
+            keep &= ((idx >> int(p)) & 1) == ((outcome >> j) & 1)
+        psi[:] = np.where(keep, psi.real * scale_re + 1j * psi.imag * scale_im, 0)
+
     def scale(self, st, f):
         st.mul_(f)
 
@@ -62,10 +81,28 @@ def main():
     rng = np.random.default_rng(seed)
     psi = (rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)).astype(ctype)
     psi /= np.linalg.norm(psi)
-    runner = ShardedRunner(n, lowered, ctype, dist, engine=OracleEngine(n - g, ctype))
+    functional = len(sys.argv) > 5 and sys.argv[5] == "functional"
     nl = n - g
-    runner.a.copy_(torch.from_numpy(psi[rank * 2 ** nl:(rank + 1) * 2 ** nl].copy()))
-    runner.step()
+    if functional:
+        # three gate segments separated by a Projection and a Measure that touch rank bits and local bits
+        from hybridq_b200.simulate import _apply_projection, _apply_measure
+        from hybridq_b200.circuits import ProjectionApply, MeasureApply
+        qmap = {q: n - 1 - q for q in range(n)}
+        cut = [len(lowered) // 3, 2 * len(lowered) // 3]
+        runner = ShardedRunner(n, lowered[:cut[0]], ctype, dist, engine=OracleEngine(n - g, ctype))
+        runner.a.copy_(torch.from_numpy(psi[rank * 2 ** nl:(rank + 1) * 2 ** nl].copy()))
+        runner.step()
+        _apply_projection(ProjectionApply((0, n - 2), "10"), runner, qmap)
+        runner.replan(lowered[cut[0]:cut[1]])
+        runner.step()
+        np.random.seed(seed)
+        _apply_measure(MeasureApply((n - 1, 1, 4)), runner, qmap)
+        runner.replan(lowered[cut[1]:])
+        runner.step()
+    else:
+        runner = ShardedRunner(n, lowered, ctype, dist, engine=OracleEngine(n - g, ctype))
+        runner.a.copy_(torch.from_numpy(psi[rank * 2 ** nl:(rank + 1) * 2 ** nl].copy()))
+        runner.step()
     n2 = runner.norm2()
     full = runner.gather()
     if rank == 0:

@@ -12,11 +12,11 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _launch(world, n, ctype, seed, out):
+def _launch(world, n, ctype, seed, out, *extra):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world * 10 + seed),
-           str(ROOT / "tests" / "dist_worker.py"), str(n), ctype, str(seed), str(out)]
+           str(ROOT / "tests" / "dist_worker.py"), str(n), ctype, str(seed), str(out), *extra]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
 
@@ -35,6 +35,28 @@ def test_sharded_evolution_matches_oracle(tmp_path, oracle, world, seed):
     assert np.abs(z["out"] - ref).max() < 1e-12
     assert abs(float(z["norm2"]) - 1) < 1e-12
     assert int(z["exchanges"]) >= 1 and int(z["exchanges"]) <= int(z["crossing"]) + 2
+
+
+@pytest.mark.parametrize("world,seed", [(2, 5), (4, 7)])
+def test_sharded_projection_and_measure(tmp_path, oracle, world, seed):
+    """Projection and Measure on a sharded state (targets on rank bits and on local bits) between gate
+    segments: same result as the single-process restatement with the same numpy seed."""
+    from hybridq_b200.circuits import sharded_circuit, to_positions
+    n, ctype = 10, "complex128"
+    out = tmp_path / "res.npz"
+    _launch(world, n, ctype, seed, out, "functional")
+    z = np.load(out)
+    g = int(np.log2(world))
+    lowered, _ = to_positions(sharded_circuit(n, g, depth=5, frac_global=0.3, seed=seed), qubits=list(range(n)))
+    cut = [len(lowered) // 3, 2 * len(lowered) // 3]
+    psi = oracle.evolve_oracle(z["psi"], lowered[:cut[0]])
+    psi = oracle.numpy_project(psi, [n - 1 - 0, n - 1 - (n - 2)], [1, 0])
+    psi = oracle.evolve_oracle(psi, lowered[cut[0]:cut[1]])
+    np.random.seed(seed)
+    psi, _ = oracle.numpy_measure(psi, [n - 1 - q for q in (n - 1, 1, 4)])
+    psi = oracle.evolve_oracle(psi, lowered[cut[1]:])
+    assert np.abs(z["out"] - psi).max() < 1e-12
+    assert abs(float(z["norm2"]) - 1) < 1e-12
 
 
 def test_schedule_model_single_process(oracle):
