@@ -86,7 +86,7 @@ __device__ __forceinline__ void gate_mma_rows_f32(float4* tile, const HqGateDesc
   for (uint32_t it = 0; it < n_iter; it += UNR) {
     uint32_t sb[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
+    for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);   // measured: the load beats iter_offset() here
     if (amp)
       mma_iter_f32_amp<KS, UNR, (KS <= HQ_MMA_BREG_KS), (KS >= 16)>(reinterpret_cast<float2*>(tile), sb, row8, xo, bf, breg, xtab);
     else
@@ -128,7 +128,7 @@ __device__ __forceinline__ void gate_mma_rows_f64(double2* tile, const HqGateDes
   for (uint32_t it = 0; it < n_iter; it += UNR) {
     uint32_t sb[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);
+    for (int u = 0; u < UNR; ++u) sb[u] = st ^ __ldg(&g->tbl_iter[it + u]);   // measured: the load beats iter_offset() here
     dmma_iter_f64<KS, UNR, (KS <= HQ_MMA_BREG_KS)>(tile, sb, xo, bf, breg, xtab);
   }
 }

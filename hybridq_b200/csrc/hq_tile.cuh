@@ -145,6 +145,21 @@ HQ_HD uint32_t scatter_bits(uint32_t w, const uint8_t* q, int from, int to) {
   return u;
 }
 
+// Iteration offsets without loads: every lane table is GF(2)-linear in its index, so
+//   tbl_iter[it] = XOR over the set bits b of it of tbl_iter[1 << b].
+// The four basis entries are read once per gate; inside the loops the offset is a handful of
+// (warp-uniform) logic operations instead of a dependent L1 load in front of every shared load.
+struct IterBasis { uint32_t b[4]; };
+HQ_DEV IterBasis load_iter_basis(const uint16_t* __restrict__ tbl) {
+  IterBasis r;
+  HQ_UNROLL
+  for (int i = 0; i < 4; ++i) r.b[i] = HQ_LDG(&tbl[1 << i]);
+  return r;
+}
+HQ_DEV uint32_t iter_offset(const IterBasis& r, uint32_t it) {
+  return ((it & 1u) ? r.b[0] : 0u) ^ ((it & 2u) ? r.b[1] : 0u) ^ ((it & 4u) ? r.b[2] : 0u) ^ ((it & 8u) ? r.b[3] : 0u);
+}
+
 // ---------------------------------------------------------------------------------------
 // register path: the slot of unit m of work item w = tid + (it << 8) is
 //   tbl_thread[tid] ^ tbl_iter[it] ^ tbl_x[m]      (see HqGateDesc)
@@ -162,6 +177,7 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc* __restrict__ g, const
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
   const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  const IterBasis ib = load_iter_basis(g->tbl_iter);
   uint32_t xo[DIM];
   HQ_UNROLL
   for (int m = 0; m < DIM; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
@@ -174,7 +190,7 @@ HQ_DEV void gate_small_f32(float4* tile, const HqGateDesc* __restrict__ g, const
 
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
+    const uint32_t sb = st ^ iter_offset(ib, it);
     float4 in[DIM];
     HQ_UNROLL
     for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xo[m]];
@@ -237,12 +253,13 @@ HQ_DEV void gate_fast_f32_k2(float4* tile, const HqGateDesc* __restrict__ g, con
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
   const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  const IterBasis ib = load_iter_basis(g->tbl_iter);
   uint32_t xo[4];
   HQ_UNROLL
   for (int m = 0; m < 4; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
+    const uint32_t sb = st ^ iter_offset(ib, it);
     // amplitude pairs (re, im) of the even / odd group and the same multiplied by i: (-im, re)
     F2 e[4], o[4], ie[4], io[4];
     HQ_UNROLL
@@ -281,6 +298,7 @@ HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc* __restrict__ g, c
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
   const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  const IterBasis ib = load_iter_basis(g->tbl_iter);
   uint32_t xo[UD];
   HQ_UNROLL
   for (int m = 0; m < UD; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
@@ -293,7 +311,7 @@ HQ_DEV void gate_small_f32_low(float4* tile, const HqGateDesc* __restrict__ g, c
 
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
+    const uint32_t sb = st ^ iter_offset(ib, it);
     float4 in[UD];
     HQ_UNROLL
     for (int m = 0; m < UD; ++m) in[m] = tile[sb ^ xo[m]];
@@ -343,6 +361,7 @@ HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc* __restrict__ g, cons
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
   const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  const IterBasis ib = load_iter_basis(g->tbl_iter);
   uint32_t xo[DIM];
   HQ_UNROLL
   for (int m = 0; m < DIM; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
@@ -355,7 +374,7 @@ HQ_DEV void gate_small_f64(double2* tile, const HqGateDesc* __restrict__ g, cons
 
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
-    const uint32_t sb = st ^ HQ_LDG(&g->tbl_iter[it]);
+    const uint32_t sb = st ^ iter_offset(ib, it);
     double2 in[DIM];
     HQ_UNROLL
     for (int m = 0; m < DIM; ++m) in[m] = tile[sb ^ xo[m]];
