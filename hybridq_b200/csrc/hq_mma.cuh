@@ -51,11 +51,21 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 //      lo = x - trunc(x): LOP3 + FADD, no extra register for hi
 //   1  hi = round-to-nearest by integer add + mask, lo = x - hi: 3 instructions
 //   2  hi = cvt.rna.tf32.f32 (ptxas expands it to 4 instructions with an inf/nan guard), lo = x - hi
+//   3  like 1, and lo is rounded to nearest TF32 too (5 instructions)
 // lo always goes to the tensor core as raw fp32 bits.  Relative error per product: about 2^-20
 // (SPLIT 0) or 2^-21 (1, 2).  Measured on B200 (profiles/r01/microbench_mma_b.jsonl, 16 k = 2 gates
 // on a tile): max-abs error 3.6e-7 (SPLIT 0) vs 1.2e-7 (SPLIT 1) at the same speed, so 1 is the default.
 #ifndef HQ_TF32_SPLIT
 #define HQ_TF32_SPLIT 1
+#endif
+// The tensor core adds into its fp32 accumulator with truncation (round toward zero): chaining the big
+// hi*hi products through the accumulator shrinks every amplitude by about one ulp per gate -- measured
+// norm^2 - 1 = -1.0e-4 after 600 k = 3 gates against -4e-8 on the FMA path (tools/norm_drift.py).  With
+// HQ_MMA_ACC_OUTSIDE (default) every hi*hi product is issued with a zero accumulator and summed with
+// round-to-nearest FADDs, and only the small correction terms (lo*hi, hi*lo) are chained inside the
+// tensor core (the scheme of Ootomo & Yokota, "Recovering single precision accuracy from Tensor Cores").
+#ifndef HQ_MMA_ACC_OUTSIDE
+#define HQ_MMA_ACC_OUTSIDE 1
 #endif
 template <int SPLIT>
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
@@ -65,10 +75,29 @@ __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) 
   } else if (SPLIT == 1) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
-  } else {
+  } else if (SPLIT == 2) {
     hi = tf32_rna(x);
     lo = __float_as_uint(x - __uint_as_float(hi));
+  } else {
+    // 3: hi and lo both rounded to nearest TF32 by add + mask, so that nothing is left to the tensor
+    // core's truncation of its operands (which is biased toward zero): 5 instructions
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
   }
+}
+
+// the hi*hi product of one k-step: chained in the tensor core (d) or, by default, computed against a zero
+// accumulator and added to `big` with round-to-nearest FADDs
+__device__ __forceinline__ void mma_main(float (&d)[4], float (&big)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#if HQ_MMA_ACC_OUTSIDE
+  float m[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_tf32(m, a, b0, b1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) big[e] += m[e];
+#else
+  (void)big;
+  mma_tf32(d, a, b0, b1);
+#endif
 }
 
 // Order of a lane's four A values inside a 16-byte complex64 unit (re_even, im_even, re_odd,
@@ -112,9 +141,12 @@ __device__ __forceinline__ void mma_iter_f32_unit(float4* tile, const uint32_t (
     }
 #pragma unroll(KS >= 8 ? 1 : KS)
   for (int j = 0; j < KS; ++j) {
-    float d[UNR][4];
+    float d[UNR][4], big[UNR][4];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+    for (int u = 0; u < UNR; ++u) {
+      d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+      big[u][0] = big[u][1] = big[u][2] = big[u][3] = 0.f;
+    }
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       const float4 b = BREG ? breg[(KS >= 8 ? 0 : s * KS + j)] : __ldg(&bf[(s * KS + j) * 32]);
@@ -128,7 +160,7 @@ __device__ __forceinline__ void mma_iter_f32_unit(float4* tile, const uint32_t (
           for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[u][s][e], h[e], l[e]);
           mma_tf32(d[u], l, bh0, bh1);
           mma_tf32(d[u], h, bl0, bl1);
-          mma_tf32(d[u], h, bh0, bh1);
+          mma_main(d[u], big[u], h, bh0, bh1);
         }
       } else {
 #pragma unroll
@@ -136,9 +168,15 @@ __device__ __forceinline__ void mma_iter_f32_unit(float4* tile, const uint32_t (
 #pragma unroll
         for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bl0, bl1);
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bh0, bh1);
+        for (int u = 0; u < UNR; ++u) mma_main(d[u], big[u], hi[u][s], bh0, bh1);
       }
     }
+#if HQ_MMA_ACC_OUTSIDE
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[u][e] += big[u][e];
+#endif
     const uint32_t xj = KS >= 8 ? uint32_t(__ldg(&xtab[4 * j])) : xo[KS >= 8 ? 0 : j];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) tile[sb[u] ^ xj] = make_float4(d[u][0], d[u][1], d[u][2], d[u][3]);
@@ -169,9 +207,12 @@ __device__ __forceinline__ void mma_iter_f32_amp(float2* tile, const uint32_t (&
     }
 #pragma unroll(KS >= 8 ? 1 : KS)
   for (int j = 0; j < KS; ++j) {
-    float d[UNR][4];
+    float d[UNR][4], big[UNR][4];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+    for (int u = 0; u < UNR; ++u) {
+      d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+      big[u][0] = big[u][1] = big[u][2] = big[u][3] = 0.f;
+    }
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       const float4 b = BREG ? breg[(KS >= 8 ? 0 : s * KS + j)] : __ldg(&bf[(s * KS + j) * 32]);
@@ -185,7 +226,7 @@ __device__ __forceinline__ void mma_iter_f32_amp(float2* tile, const uint32_t (&
           for (int e = 0; e < 4; ++e) tf32_split<SPLIT>(raw[u][s][e], h[e], l[e]);
           mma_tf32(d[u], l, bh0, bh1);
           mma_tf32(d[u], h, bl0, bl1);
-          mma_tf32(d[u], h, bh0, bh1);
+          mma_main(d[u], big[u], h, bh0, bh1);
         }
       } else {
 #pragma unroll
@@ -193,9 +234,15 @@ __device__ __forceinline__ void mma_iter_f32_amp(float2* tile, const uint32_t (&
 #pragma unroll
         for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bl0, bl1);
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) mma_tf32(d[u], hi[u][s], bh0, bh1);
+        for (int u = 0; u < UNR; ++u) mma_main(d[u], big[u], hi[u][s], bh0, bh1);
       }
     }
+#if HQ_MMA_ACC_OUTSIDE
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[u][e] += big[u][e];
+#endif
     const uint32_t xj = KS >= 8 ? uint32_t(__ldg(&xtab[4 * j])) : xo[KS >= 8 ? 0 : j];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {

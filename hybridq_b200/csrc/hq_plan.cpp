@@ -376,11 +376,11 @@ int union_k(uint64_t a, uint64_t b) { return __builtin_popcountll(a | b); }
 
 // Greedy merging of an ordered gate list (all inside one tile).
 // Cost of one kernel matrix of k qubits inside a saturated pass, in microseconds at n = 30 (complex64)
-// / n = 29 (complex128), measured on B200 (profiles/r01/sweep_slope_b_breg4_k1d3.jsonl): the FMA
+// / n = 29 (complex128), measured on B200 (profiles/r01/sweep_slope_b_breg4_k1d3.jsonl, sweep_slope_e_acc_outside.jsonl): the FMA
 // paths (constant-bank FFMA2 slots for complex64 k = 2, row pairs for complex128) and the tensor-core
 // path (3xTF32 / FP64 mma.sync).  Only the ratios matter.
 int measured_cost(int dtype, bool mma_on, int mma_min_k, int k) {
-  static const int c64_fma[5] = {0, 660, 665, 2180, 5280}, c64_mma[5] = {0, 660, 940, 1220, 2120};
+  static const int c64_fma[5] = {0, 660, 665, 2180, 5280}, c64_mma[5] = {0, 660, 940, 1255, 2420};
   static const int c128_fma[5] = {0, 620, 1255, 2650, 7190}, c128_mma[5] = {0, 620, 720, 1160, 2320};
   if (k < 1) return 0;
   if (k > 4) return 1 << 30;

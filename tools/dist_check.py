@@ -78,6 +78,27 @@ if rank == 0:
     lines.append(rec)
 dist.barrier()
 
+# Projection and Measure on the sharded state (targets on rank bits and local bits), every rank seeds numpy alike
+from hybridq_b200.circuits import ProjectionApply, MeasureApply  # noqa: E402
+n = 22
+g1 = matching_circuit(n, depth=3, seed=6)
+circ = g1 + [ProjectionApply((0, 7), "10")] + matching_circuit(n, depth=2, seed=7) + [MeasureApply((1, 0, 12))] + \
+    matching_circuit(n, depth=2, seed=8)
+np.random.seed(99)
+shard = hb.simulate(circ, initial_state="+" * n, complex_type="complex128")
+full_parts = [torch.empty(shard.size, dtype=torch.complex128, device="cuda") for _ in range(world)]
+dist.all_gather(full_parts, torch.from_numpy(shard.reshape(-1).copy()).cuda())
+if rank == 0:
+    np.random.seed(99)
+    ref = hb.simulate(circ, initial_state="+" * n, complex_type="complex128", shard=False).reshape(-1)
+    got = torch.cat(full_parts).cpu().numpy()
+    err = float(np.abs(got - ref).max())
+    rec = {"simulate_sharded_functional_n": n, "world": world, "max_abs_err_vs_1gpu": err, "ok": bool(err <= 1e-12),
+           "norm2": float(np.vdot(got, got).real)}
+    print(json.dumps(rec), flush=True)
+    lines.append(rec)
+dist.barrier()
+
 if args.timing_size:
     n = args.timing_size
     gates = sharded_circuit(n, g, depth=20, frac_global=0.2, seed=n)
