@@ -413,6 +413,25 @@ class SingleGpuRunner:
         worst = min(single.values())
         out["single_gate"] = {"kernel": "hq_direct_kernel", "GBps": single, "min_GBps": worst,
                               "min_frac_of_measured_peak": worst / peak, "min_frac_of_8TBs": worst / 8000.0}
+        # lone k = 3..5 gates on random bits: the tensor-core path of the tile kernel (3xTF32 mma.sync)
+        tensor = {}
+        for k in (3, 4, 5):
+            pos = sorted(int(x) for x in rng.permutation(self.n)[:k])
+            plan = self.hb.Plan([(haar_unitary(2 ** k, rng), pos)], self.n, CTYPE)
+            for _ in range(2):
+                plan.run(self.state)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                plan.run(self.state)
+            e1.record()
+            torch.cuda.synchronize()
+            tensor[f"k{k}_random_bits"] = bytes_pass / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e9
+        out["tensor_core_gates"] = {"kernel": "hq_tile_kernel, mma.sync 3xTF32 gate path", "GBps": tensor,
+                                    "tflops_3xtf32": {f"k{k}": 3 * 8.0 * 2 ** k * 2 ** self.n /
+                                                      (bytes_pass / (tensor[f"k{k}_random_bits"] * 1e9)) / 1e12
+                                                      for k in (3, 4, 5)}}
         kms = self.kernel_time_ms(reps=1)
         out["fused_fp32_tflops"] = self.plan.flops / (kms * 1e-3) / 1e12
         out["fp32_tflops_nominal_peak"] = 148 * 128 * 2 * 1.965e9 / 1e12

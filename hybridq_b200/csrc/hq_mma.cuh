@@ -89,11 +89,14 @@ __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) 
 // the hi*hi product of one k-step: chained in the tensor core (d) or, by default, computed against a zero
 // accumulator and added to `big` with round-to-nearest FADDs
 __device__ __forceinline__ void mma_main(float (&d)[4], float (&big)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-#if HQ_MMA_ACC_OUTSIDE
+#if HQ_MMA_ACC_OUTSIDE == 1
   float m[4] = {0.f, 0.f, 0.f, 0.f};
   mma_tf32(m, a, b0, b1);
 #pragma unroll
   for (int e = 0; e < 4; ++e) big[e] += m[e];
+#elif HQ_MMA_ACC_OUTSIDE == 2
+  (void)d;
+  mma_tf32(big, a, b0, b1);     // the big products chained among themselves, apart from the small terms
 #else
   (void)big;
   mma_tf32(d, a, b0, b1);

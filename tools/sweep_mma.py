@@ -72,9 +72,6 @@ for ctype, n in (("complex64", args.n64), ("complex128", args.n128)):
     for label, opts in variants:
         plan = hb.Plan(lowered, n, ctype, opts)
         ms = timed(plan, st, args.reps)
-        ks = {}
-        for i in range(plan.n_passes):
-            pass
         print(json.dumps({"test": "circuit", "ctype": ctype, "n": n, "variant": label, "ms_per_step": ms,
                           "gate_applies_per_s": plan.n_gates / ms * 1e3, "passes": plan.n_passes,
                           "kernel_matrices": plan.n_kernel_gates, "tflops": plan.flops / ms / 1e9}), flush=True)
