@@ -4,6 +4,7 @@
 // CPU-only test-suite can check the tile/lane/swizzle index math, the fusion planner and
 // the bit-permutation passes against the oracle without a GPU.  It is NOT a fallback: the
 // Python package never imports it and hybridq_b200 fails loudly without the CUDA library.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -328,6 +329,80 @@ int hq_emu_bitperm(int dtype, unsigned n, const unsigned* perm, const int* opts,
   emu_plan(plan, state_interleaved);
   if (info_out) info_out[0] = int(plan.passes.size());
   return 0;
+}
+
+// Shared-memory bank model of the gate loops (host-logic tests): for every kernel matrix of the plan, the
+// number of wavefronts its 16-byte accesses need per warp instruction against the ideal of 4 (a quarter-warp
+// is served in one wavefront when its 8 lanes hit 8 distinct 16-byte bank groups = slot & 7; the complex64
+// amplitude path issues 8-byte accesses, served per half-warp of 16 lanes over 16 bank pairs).
+// out[3 g] = gate kind, out[3 g + 1] = ideal wavefronts, out[3 g + 2] = modelled wavefronts (first row set /
+// first iteration of every warp, all k-steps / group members).  Returns the number of gates or -1.
+int hq_emu_bank_model(int dtype, unsigned n, unsigned n_gates, const unsigned* ks, const unsigned* pos_flat,
+                      const int* opts, unsigned* out, int out_len) {
+  std::vector<hq::GateIn> gates(n_gates);
+  size_t po = 0;
+  for (unsigned g = 0; g < n_gates; ++g) {
+    const unsigned k = ks[g];
+    gates[g].k = k;
+    gates[g].pos.assign(pos_flat + po, pos_flat + po + k);
+    gates[g].U.assign(size_t(1) << (2 * k), std::complex<double>(0, 0));
+    for (size_t i = 0; i < (size_t(1) << k); ++i) gates[g].U[i * ((size_t(1) << k) + 1)] = 1.0;
+    po += k;
+  }
+  hq::Plan plan;
+  if (hq::plan_build(plan, dtype, n, gates, make_opts(opts))) return -1;
+  if (int(plan.n_kernel_gates) * 3 > out_len) return -1;
+  const HqGateDesc* gd = reinterpret_cast<const HqGateDesc*>(plan.program.data());
+  for (unsigned gi = 0; gi < plan.n_kernel_gates; ++gi) {
+    const HqGateDesc& g = gd[gi];
+    unsigned ideal = 0, actual = 0;
+    auto quarter = [&](const uint32_t* slots) {       // 8 lanes, 16-byte accesses
+      unsigned cnt[8] = {0};
+      unsigned worst = 0;
+      for (int l = 0; l < 8; ++l) worst = std::max(worst, ++cnt[slots[l] & 7u]);
+      ideal += 1;
+      actual += worst;
+    };
+    auto half = [&](const uint32_t* aslots) {         // 16 lanes, 8-byte accesses: bank pair = amplitude slot & 15
+      unsigned cnt[16] = {0};
+      unsigned worst = 0;
+      for (int l = 0; l < 16; ++l) worst = std::max(worst, ++cnt[aslots[l] & 15u]);
+      ideal += 1;
+      actual += worst;
+    };
+    if (g.kind == HQ_GATE_MMA) {
+      const int KS = (1 << g.k) / 4;
+      for (uint32_t warp = 0; warp < g.mma_warps; ++warp)
+        for (int s = 0; s < KS; ++s) {
+          uint32_t slots[32];
+          for (int lane = 0; lane < 32; ++lane)
+            slots[lane] = uint32_t(g.tbl_thread[warp * 32 + uint32_t(lane)]) ^ uint32_t(g.tbl_x[(lane & 3) + 4 * s]);
+          if (g.mma_amp) {
+            for (int h = 0; h < 2; ++h) {
+              half(slots + 16 * h);
+              uint32_t other[16];
+              for (int l = 0; l < 16; ++l) other[l] = slots[16 * h + l] ^ g.mma_row8;
+              half(other);
+            }
+          } else {
+            for (int q = 0; q < 4; ++q) quarter(slots + 8 * q);
+          }
+        }
+    } else if (g.kind == HQ_GATE_SMALL) {
+      const bool low = dtype == HQ_DTYPE_C64 && g.tpos[0] == 0;
+      const int KK = int(g.k) - (low ? 1 : 0);
+      for (int m = 0; m < (1 << KK); ++m)
+        for (int w = 0; w < HQ_THREADS / 8; ++w) {
+          uint32_t slots[8];
+          for (int l = 0; l < 8; ++l) slots[l] = uint32_t(g.tbl_thread[w * 8 + l]) ^ uint32_t(g.tbl_x[m]);
+          quarter(slots);
+        }
+    }
+    out[3 * gi] = g.kind;
+    out[3 * gi + 1] = ideal;
+    out[3 * gi + 2] = actual;
+  }
+  return int(plan.n_kernel_gates);
 }
 
 // planner introspection for host-logic tests: passes as flat records

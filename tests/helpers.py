@@ -111,6 +111,18 @@ class Emu:
             raise RuntimeError(err.value.decode())
         return st, info[0]
 
+    def bank_model(self, dtype, n, gates_pos, opts=None):
+        """[(kind, ideal wavefronts, modelled wavefronts)] per kernel matrix (hq_emu_bank_model)."""
+        ks = np.array([len(p) for p in gates_pos], dtype=np.uint32)
+        pos = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.uint32) for p in gates_pos]))
+        out = np.zeros(3 * (len(gates_pos) + 1), dtype=np.uint32)
+        ng = self.lib.hq_emu_bank_model(dtype, n, len(gates_pos), ks.ctypes.data_as(ctypes.c_void_p),
+                                        pos.ctypes.data_as(ctypes.c_void_p), _emu_opts(opts),
+                                        out.ctypes.data_as(ctypes.c_void_p), out.size)
+        if ng < 0:
+            raise RuntimeError("bank model failed")
+        return [tuple(int(x) for x in out[3 * i:3 * i + 3]) for i in range(ng)]
+
     def plan(self, dtype, n, gates_pos, opts=None):
         """Planner only: returns list of passes {tile_bits, n_high, n_gates, has_perm, high_pos, gate_ids}."""
         ks = np.array([len(p) for p in gates_pos], dtype=np.uint32)

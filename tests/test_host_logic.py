@@ -55,3 +55,34 @@ def test_simulate_argument_errors_mirror_the_reference():
         hb.simulate(gates, initial_state="0", tensor_only=True)
     with pytest.raises(NotImplementedError):
         hb.simulate(gates, initial_state="0", optimize="tn")
+
+
+def test_lane_mapping_is_bank_conflict_free():
+    """The planner's lane choices against a bank model of the shared-memory accesses (hq_tile.cuh swizzle with 7
+    distinct bank vectors): FMA register-path gates are conflict-free for every target set; tensor-core gates
+    are conflict-free unless their lane bits are forced onto colliding vectors (k = 2 with one of the 5
+    colliding unit-bit pairs 0/7, 1/8, 2/9, 3/10, 4/11) -- and then cost at most 2 wavefronts per quarter-warp."""
+    from helpers import Emu
+    emu = Emu()
+    rng = np.random.default_rng(2)
+    collide = {(0, 7), (1, 8), (2, 9), (3, 10), (4, 11)}
+    for dtype, V, T in ((0, 1, 13), (1, 0, 12)):
+        n = T
+        for k in (1, 2, 3, 4):
+            for _ in range(40):
+                pos = sorted(int(x) for x in rng.permutation(n)[:k])
+                # two gates on the same bits, unmerged, so that k = 2 keeps the requested kind
+                for mma in (0, 2):
+                    if mma and k < 2:
+                        continue
+                    res = emu.bank_model(dtype, n, [pos, pos], (T, 1, 1, 0, 0, 0, -1, 0, mma))
+                    for kind, ideal, actual in res:
+                        if kind == 3:       # HQ_GATE_MMA
+                            unit_bits = [p - V for p in pos if p - V >= 0]
+                            forced = k == 2 and len(unit_bits) == 2 and tuple(unit_bits) in collide
+                            if forced:
+                                assert actual <= 2 * ideal, (dtype, pos, ideal, actual)
+                            else:               # unit path and complex64 amplitude path (8-byte accesses)
+                                assert actual == ideal, (dtype, pos, ideal, actual)
+                        elif kind == 0:     # register path
+                            assert actual == ideal, (dtype, pos, ideal, actual)
