@@ -86,3 +86,22 @@ def test_lane_mapping_is_bank_conflict_free():
                                 assert actual == ideal, (dtype, pos, ideal, actual)
                         elif kind == 0:     # register path
                             assert actual == ideal, (dtype, pos, ideal, actual)
+
+
+def test_merging_follows_the_measured_cost_table():
+    """In-pass merging (hq_plan.cpp measured_cost): with the tensor-core path two k = 2 gates sharing a bit
+    become one k = 3 matrix, disjoint k = 2 gates stay apart (a k = 4 matrix costs more than two k = 2 ones),
+    a 1-qubit gate is absorbed by a neighbour; with FMA paths only nothing grows beyond k = 2."""
+    from helpers import Emu
+    emu = Emu()
+    n = 14
+    for dtype in (0, 1):
+        def mats(gates, opts=None):
+            return sum(p["n_kernel_gates"] for p in emu.plan(dtype, n, gates, opts))
+        assert mats([[3, 5], [5, 8]]) == 1                      # chain -> k = 3
+        assert mats([[3, 5], [7, 8]]) == 2                      # disjoint -> two matrices
+        assert mats([[3, 5], [5]]) == 1 and mats([[4], [4, 9]]) == 1
+        assert mats([[3, 5], [5, 8], [8, 3]]) == 1              # triangle on 3 bits -> one k = 3
+        assert mats([[3, 5], [5, 8]], (0, -1, 1, 0, 0, -1, -1, 1, 0)) == 2      # FMA only: no k = 3 merge
+        assert mats([[3, 5], [5, 8]], (0, -1, 1, 0, 0, 0, -1, 1, -1)) == 2      # merging off
+        assert mats([[1, 2, 3], [2, 3, 4]]) == 1                # two k = 3 sharing two bits -> k = 4
