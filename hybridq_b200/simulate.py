@@ -399,7 +399,11 @@ def _apply_measure(gate, state: DeviceState, qmap: dict, renormalize: bool = Tru
     k = len(qubits)
     pos = [qmap[q] for q in reversed(qubits)]           # outcome bit j <-> qubits[k-1-j]
     sums = state.marginal(pos)
-    probs = sums.sum(axis=1).astype(np.float32 if state.complex_type == np.complex64 else np.float64)
+    probs = sums.sum(axis=1)
+    # numpy.random.choice normalises its cdf itself (cdf /= cdf[-1]) but first rejects a p that is off 1 by
+    # more than sqrt(eps); normalising here leaves the draw unchanged and keeps deep complex64 circuits,
+    # whose norm drifts by a few 1e-5 per thousand gates on the tensor-core path, from tripping that check
+    probs = (probs / probs.sum()).astype(np.float32 if state.complex_type == np.complex64 else np.float64)
     if hasattr(state, "broadcast_int"):                 # sharded state: rank 0 draws for everybody
         outcome = state.broadcast_int(int(np.random.choice(2 ** k, p=probs)) if state.rank == 0 else 0)
     else:
