@@ -136,6 +136,7 @@ import numpy as np
 from oracle import oracle as O
 import bench
 variant, n, n_sample, steps, warmup = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+bench.N_BASE, bench.SCALING = int(sys.argv[6]), sys.argv[7]
 core = O.RefCore(variant)
 _, _, lowered, _ = bench.workload(1 if n == bench.N_BASE else 2 ** (n - bench.N_BASE))
 gates = [(U.astype(bench.CTYPE), p) for U, p in lowered[:n_sample]]
@@ -168,7 +169,8 @@ def run_reference_cpu(n: int, n_sample: int, steps: int, warmup: int, timeout: f
             continue
         try:
             r = subprocess.run([sys.executable, "-c", _CHILD.format(root=str(ROOT)), variant, str(n), str(n_sample),
-                                str(steps), str(warmup)], env=env, capture_output=True, text=True, timeout=timeout)
+                                str(steps), str(warmup), str(N_BASE), SCALING], env=env, capture_output=True, text=True,
+                               timeout=timeout)
             if r.returncode != 0:
                 tried.append(f"{variant}: rc={r.returncode}")
                 continue
@@ -228,6 +230,8 @@ def main():
     args = ap.parse_args()
     global N_BASE, SCALING
     SCALING = args.scaling
+    if args.qubits:
+        N_BASE = args.qubits
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -246,8 +250,6 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
-    if args.qubits:
-        N_BASE = args.qubits
     n, gates, lowered, name = workload(world)
     steps, warmup = args.steps, max(args.warmup, 3)
     state_bytes = (2 ** n) * 8
