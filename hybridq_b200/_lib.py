@@ -97,6 +97,10 @@ _proto("hq_marginal_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, _u32p,
        ctypes.POINTER(ctypes.c_double), _vp)
 _proto("hq_project_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes.c_uint, ctypes.c_uint,
        ctypes.c_double, ctypes.c_double, _vp)
+_proto("hq_marginal_cond_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes.c_uint, ctypes.c_uint64,
+       ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), _vp)
+_proto("hq_project_mask_dev", ctypes.c_int, _vp, ctypes.c_int, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint64,
+       ctypes.c_double, ctypes.c_double, _vp)
 _proto("hq_plan_create", _vp, ctypes.c_int, ctypes.c_uint, ctypes.c_uint, _u32p, _u32p,
        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(PlanOptions))
 _proto("hq_plan_create_bitperm", _vp, ctypes.c_int, ctypes.c_uint, _u32p, ctypes.POINTER(PlanOptions))
@@ -109,6 +113,12 @@ _proto("hq_plan_pass_info", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int
 _proto("hq_plan_pass_gates", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int)
 _proto("hq_plan_run", ctypes.c_int, _vp, _vp, _vp)
 _proto("hq_plan_run_range", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp)
+_proto("hq_plan_run_range_xchg", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_uint,
+       _u32p, ctypes.POINTER(_vp), _vp)
+_proto("hq_ipc_get_handle", ctypes.c_int, _vp, _vp)
+_proto("hq_ipc_open", ctypes.c_int, _vp, ctypes.POINTER(_vp))
+_proto("hq_ipc_close", ctypes.c_int, _vp)
+_proto("hq_set_ring", ctypes.c_int, ctypes.c_int)
 _proto("hq_set_tuning", ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int)
 _proto("hq_launch_count", ctypes.c_uint64)
 _proto("hq_launch_count_reset", None)
@@ -120,8 +130,9 @@ EXPORTED = [
     "hq_free", "hq_host_alloc", "hq_host_free", "hq_memcpy_h2d", "hq_memcpy_d2h", "hq_memcpy_d2d",
     "hq_stream_sync", "hq_apply_U_dev", "hq_apply_U_direct_dev", "hq_swap_dev", "hq_pack_dev",
     "hq_unpack_dev", "hq_init_product_dev", "hq_init_random_dev", "hq_norm2_dev", "hq_vdot_dev",
-    "hq_scale_dev", "hq_marginal_dev", "hq_project_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
+    "hq_scale_dev", "hq_marginal_dev", "hq_project_dev", "hq_marginal_cond_dev", "hq_project_mask_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
     "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_flops", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
+    "hq_plan_run_range_xchg", "hq_ipc_get_handle", "hq_ipc_open", "hq_ipc_close", "hq_set_ring",
     "hq_set_tuning", "hq_launch_count", "hq_launch_count_reset",
 ]
 

@@ -80,12 +80,15 @@ void fill_gate(hq::GateIn& g, const T* U, const unsigned* pos, unsigned k) {
 
 int g_use_direct = 1;   // single k <= 2 gate passes go to the shared-memory-free kernel
 
-int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, int first, int last, void* stream) {
+// xchg (may be null): exchange redirect applied to the write-back of the LAST pass of the range
+int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, int first, int last, void* stream,
+                    const hq::HqXchgDesc* xchg = nullptr) {
   for (int p = first; p < last; ++p) {
     const HqPassHeader& ph = plan.passes[size_t(p)].header;
-    if (ph.n_gates == 0 && !ph.has_perm) continue;
-    if (g_use_direct && ph.n_gates == 1 && !ph.has_perm && ph.max_k <= 2 && plan.n_qubits >= ph.max_k + 1) {
-      // measured (profiles/): the direct kernel runs a lone 1-/2-qubit gate at copy bandwidth
+    const hq::HqXchgDesc* xg = (xchg && xchg->s && p == last - 1) ? xchg : nullptr;
+    if (ph.n_gates == 0 && !ph.has_perm && !xg) continue;
+    if (g_use_direct && !xg && ph.n_gates == 1 && !ph.has_perm && ph.max_k <= 3 && plan.n_qubits >= ph.max_k + 1) {
+      // measured (profiles/): the direct kernel runs a lone 1-/2-/3-qubit gate at copy bandwidth
       HqGateDesc gd;
       memcpy(&gd, plan.program.data() + ph.gates_off, sizeof(gd));
       const unsigned L = ph.tile_bits - ph.n_high;
@@ -97,7 +100,7 @@ int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, in
       ++g_launches;
       continue;
     }
-    const int rc = hq::launch_tile_pass(plan.dtype, state, plan.n_qubits, d_prog, ph, stream, 0);
+    const int rc = hq::launch_pass(plan.dtype, state, plan.n_qubits, d_prog, ph, xg, stream, 0);
     if (rc) return cuda_fail("tile pass launch", rc);
     ++g_launches;
   }
@@ -406,16 +409,17 @@ int hq_vdot_dev(const void* a, const void* b, int dtype, uint64_t n_amps, double
   if (!a || !b || !re_im_host) return fail("null pointer", 1);
   return reduce_partials(1, a, b, dtype, n_amps, re_im_host, stream);
 }
-int hq_marginal_dev(const void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
-                    double* out_host, void* stream) {
+int hq_marginal_cond_dev(const void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
+                         uint64_t cond_mask, uint64_t cond_value, double* out_host, void* stream) {
   if (!state || !out_host || (k && !pos)) return fail("null pointer", 1);
-  if (k > HQ_MAX_K || k > n) return fail("too many measured bits", 1);
+  if (k > HQ_MARGINAL_MAX_K || k > n) return fail("too many measured bits in one call (at most 24; sample in chunks)", 1);
+  if (n < 64 && ((cond_mask >> n) || (cond_value & ~cond_mask))) return fail("bad condition mask / value", 1);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t bins = size_t(2) << k;
   double* d_out = nullptr;
   HQ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_out), bins * sizeof(double), s));
   int rc = int(cudaMemsetAsync(d_out, 0, bins * sizeof(double), s));
-  if (rc == 0) rc = hq::launch_marginal(dtype, state, n, pos, k, d_out, stream);
+  if (rc == 0) rc = hq::launch_marginal(dtype, state, n, pos, k, cond_mask, cond_value, d_out, stream);
   if (rc == 0) {
     ++g_launches;
     rc = int(cudaMemcpyAsync(out_host, d_out, bins * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -425,13 +429,29 @@ int hq_marginal_dev(const void* state, int dtype, unsigned int n, const unsigned
   if (rc) return cuda_fail("marginal", rc);
   return 0;
 }
-int hq_project_dev(void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
-                   unsigned int outcome, double scale_re, double scale_im, void* stream) {
-  if (!state || (k && !pos)) return fail("null pointer", 1);
-  const int rc = hq::launch_project(dtype, state, n, pos, k, outcome, scale_re, scale_im, stream);
+int hq_marginal_dev(const void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
+                    double* out_host, void* stream) {
+  return hq_marginal_cond_dev(state, dtype, n, pos, k, 0, 0, out_host, stream);
+}
+int hq_project_mask_dev(void* state, int dtype, unsigned int n, uint64_t mask, uint64_t value, double scale_re,
+                        double scale_im, void* stream) {
+  if (!state) return fail("null pointer", 1);
+  const int rc = hq::launch_project(dtype, state, n, mask, value, scale_re, scale_im, stream);
   if (rc) return cuda_fail("project", rc);
   ++g_launches;
   return 0;
+}
+int hq_project_dev(void* state, int dtype, unsigned int n, const unsigned int* pos, unsigned int k,
+                   unsigned int outcome, double scale_re, double scale_im, void* stream) {
+  if (!state || (k && !pos)) return fail("null pointer", 1);
+  if (k > 32 || k > n || (k < 32 && (outcome >> k))) return fail("bad projection bits / outcome", 1);
+  uint64_t mask = 0, value = 0;
+  for (unsigned j = 0; j < k; ++j) {
+    if (pos[j] >= n || ((mask >> pos[j]) & 1ull)) return fail("bad projection bits", 1);
+    mask |= uint64_t(1) << pos[j];
+    value |= uint64_t((outcome >> j) & 1u) << pos[j];
+  }
+  return hq_project_mask_dev(state, dtype, n, mask, value, scale_re, scale_im, stream);
 }
 int hq_scale_dev(void* state, int dtype, uint64_t n_amps, double factor, void* stream) {
   HQ_CUDA(hq::launch_scale(dtype, state, n_amps, factor, stream));
@@ -548,6 +568,62 @@ int hq_plan_run_range(hq_plan* plan, void* state, int first, int last, void* str
   }
   return run_plan_passes(pl, static_cast<const unsigned char*>(pl.d_program), state, first, last, stream);
 }
+int hq_plan_run_range_xchg(hq_plan* plan, void* state, int first, int last, unsigned int s, unsigned int mine,
+                           const unsigned int* pos, void* const* dst, void* stream) {
+  if (!plan || !state) return fail("null pointer", 1);
+  if (s == 0) return hq_plan_run_range(plan, state, first, last, stream);
+  if (s > 3 || !pos || !dst) return fail("bad exchange descriptor", 1);
+  hq::Plan& pl = plan->plan;
+  if (first < 0 || last > int(pl.passes.size()) || first > last) return fail("bad pass range", 1);
+  hq::HqXchgDesc xg;
+  memset(&xg, 0, sizeof(xg));
+  xg.s = s;
+  xg.mine = mine;
+  for (unsigned j = 0; j < s; ++j) xg.pos[j] = pos[j];
+  for (unsigned d = 0; d < (1u << s); ++d) xg.dst[d] = dst[d];
+  if (first == last) {
+    // nothing to compute before the exchange: a gate-less pass carries the redirect
+    HqPassHeader ph;
+    hq::make_identity_pass(pl.dtype, pl.n_qubits, ph);
+    const int rc = hq::launch_pass(pl.dtype, state, pl.n_qubits, nullptr, ph, &xg, stream, 0);
+    if (rc) return cuda_fail("exchange pass launch", rc);
+    ++g_launches;
+    return 0;
+  }
+  int dev = 0;
+  HQ_CUDA(cudaGetDevice(&dev));
+  if (pl.d_program && pl.device != dev) {
+    cudaFree(pl.d_program);
+    pl.d_program = nullptr;
+  }
+  if (!pl.d_program) {
+    HQ_CUDA(cudaMalloc(&pl.d_program, pl.program.size()));
+    HQ_CUDA(cudaMemcpy(pl.d_program, pl.program.data(), pl.program.size(), cudaMemcpyHostToDevice));
+    pl.device = dev;
+  }
+  return run_plan_passes(pl, static_cast<const unsigned char*>(pl.d_program), state, first, last, stream, &xg);
+}
+
+int hq_ipc_get_handle(void* dptr, void* handle_out_64) {
+  if (!dptr || !handle_out_64) return fail("null pointer", 1);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  HQ_CUDA(cudaIpcGetMemHandle(&h, dptr));
+  memcpy(handle_out_64, &h, sizeof(h));
+  return 0;
+}
+int hq_ipc_open(const void* handle_64, void** dptr) {
+  if (!handle_64 || !dptr) return fail("null pointer", 1);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, sizeof(h));
+  HQ_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int hq_ipc_close(void* dptr) {
+  HQ_CUDA(cudaIpcCloseMemHandle(dptr));
+  return 0;
+}
+
 int hq_plan_run(hq_plan* plan, void* state, void* stream) {
   if (!plan) return fail("null pointer", 1);
   return hq_plan_run_range(plan, state, 0, int(plan->plan.passes.size()), stream);
@@ -556,6 +632,11 @@ int hq_plan_run(hq_plan* plan, void* state, void* stream) {
 int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct) {
   hq::set_tuning(nbuf, ctas_per_sm);
   if (use_direct >= 0) g_use_direct = use_direct;
+  return 0;
+}
+
+int hq_set_ring(int mode) {
+  hq::set_ring(mode);
   return 0;
 }
 

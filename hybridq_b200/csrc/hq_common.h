@@ -35,7 +35,8 @@
 
 #define HQ_MAX_PER_THREAD 16   // units per thread per tile = 2^(unit bits - 8) <= 16
 #define HQ_MAX_PASS_GATES 24   // kernel matrices per pass after merging
-#define HQ_FAST_SLOTS 8        // unrolled constant-bank gate slots per pass (complex64, k = 2)
+#define HQ_FAST_SLOTS 8        // constant-bank gate slots per pass (complex64, k <= 3)
+#define HQ_FAST_MAX_K 3
 
 struct HqGateDesc {        // 1280 bytes, lives in the device program buffer (read through L1)
   uint32_t k;              // number of target bits
@@ -89,15 +90,17 @@ struct HqPassHeader {      // passed to the kernel by value (constant bank)
   // (off() deposits the bits of c at their global positions, so it splits over disjoint bits).
   uint64_t iter_off[HQ_MAX_PER_THREAD];
   uint32_t iter_swz[HQ_MAX_PER_THREAD];
-  // Fast slots (complex64): gate s < HQ_FAST_SLOTS of the pass with k = 2 and no target on
-  // amplitude bit 0 has bit s of fast_mask set and its 4x4 matrix (row-major, re/im) in
-  // fast_u[s].  The kernel unrolls the slot loop, so every matrix element is a constant-bank
-  // operand of an FFMA at a compile-time offset: on B200 a 3-register FFMA issues at 21 TFMA/s,
-  // an FFMA with a constant-bank operand at 35 TFMA/s (profiles/r01/microbench_fma.jsonl).
+  // Fast slots (complex64): kernel matrix s < HQ_FAST_SLOTS of the pass with k <= 3 on the FMA path has bit s of
+  // fast_mask set, fast_k[s] = k | (4 if matrix bit 0 is amplitude bit 0) and its 2^k x 2^k matrix (row-major,
+  // re/im) in fast_u[s].  The header is a kernel parameter, so every matrix element is a constant-bank /
+  // uniform-register operand of an FFMA2: on B200 a 3-register FFMA issues at 21 TFMA/s, one with a
+  // constant-bank operand at 35 TFMA/s (profiles/r01/microbench_fma.jsonl).
   uint32_t fast_mask;
   uint32_t reserved2;
-  float fast_u[HQ_FAST_SLOTS][32];
+  uint8_t fast_k[HQ_FAST_SLOTS];
+  float fast_u[HQ_FAST_SLOTS][2 << (2 * HQ_FAST_MAX_K)];
 };
 
 static_assert(sizeof(HqGateDesc) == 624 + 96 + 512 + 32 + 16, "HqGateDesc layout");
-static_assert(sizeof(HqPassHeader) == 256 + 8 + 4 * 32 * HQ_FAST_SLOTS, "HqPassHeader layout");
+static_assert(sizeof(HqPassHeader) == 256 + 8 + HQ_FAST_SLOTS + 4 * 128 * HQ_FAST_SLOTS, "HqPassHeader layout");
+static_assert(sizeof(HqPassHeader) + 256 <= 32764, "the pass header travels as a kernel parameter (large-parameter limit)");

@@ -15,16 +15,7 @@
 namespace {
 
 void emu_fast_slot(float4* tile, int s, const HqGateDesc* g, const HqPassHeader& ph, int Tu, int tid) {
-  switch (s) {
-    case 0: hq::gate_fast_f32_k2<0>(tile, g, ph, Tu, tid); break;
-    case 1: hq::gate_fast_f32_k2<1>(tile, g, ph, Tu, tid); break;
-    case 2: hq::gate_fast_f32_k2<2>(tile, g, ph, Tu, tid); break;
-    case 3: hq::gate_fast_f32_k2<3>(tile, g, ph, Tu, tid); break;
-    case 4: hq::gate_fast_f32_k2<4>(tile, g, ph, Tu, tid); break;
-    case 5: hq::gate_fast_f32_k2<5>(tile, g, ph, Tu, tid); break;
-    case 6: hq::gate_fast_f32_k2<6>(tile, g, ph, Tu, tid); break;
-    default: hq::gate_fast_f32_k2<7>(tile, g, ph, Tu, tid); break;
-  }
+  hq::gate_fast_f32<-1, 3>(tile, g, ph, uint32_t(s), Tu, tid);
 }
 void emu_fast_slot(double2*, int, const HqGateDesc*, const HqPassHeader&, int, int) {}
 
@@ -208,7 +199,7 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
     }
     for (uint32_t gi = 0; gi < ph.n_gates; ++gi) {
       const HqGateDesc* g = gates + gi;
-      if (V == 1 && ph.max_k <= 3 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
+      if (V == 1 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
         for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
       } else if (g->kind == HQ_GATE_MMA) {
         emu_mma_gate(tile.data(), g, prog);

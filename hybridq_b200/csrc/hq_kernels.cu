@@ -28,6 +28,9 @@
 #ifndef HQ_MMA_BREG_KS
 #define HQ_MMA_BREG_KS 4  // gates with 2^k / 4 <= this keep their B fragments in registers for the whole gate
 #endif
+#ifndef HQ_K1F_BLOCKS
+#define HQ_K1F_BLOCKS 2   // resident CTAs per SM of the k <= 3 complex64 tile kernel (128 registers: the k = 3 FFMA2 slots keep 16 accumulator pairs)
+#endif
 #ifndef HQ_K1D_BLOCKS
 #define HQ_K1D_BLOCKS 3   // resident CTAs per SM of the k <= 3 complex128 tile kernel (measured: 134.6 vs 142.4 ms/step)
 #endif
@@ -200,47 +203,95 @@ __device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g,
   }
 }
 
-template <int S, int MAXK>
-__device__ __forceinline__ void fast_slot(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
-                                          const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
-  if (S < int(n_gates)) {
-    const HqGateDesc* g = gates + S;
-    if ((ph.fast_mask >> S) & 1u) {
-      gate_fast_f32_k2<S>(tile, g, ph, Tu, tid);
-    } else {
-      gate_small_generic<MAXK, MAXK>(tile, g, __ldg(&g->k), __ldg(&g->kind), prog, __ldg(&g->mat_off), Tu, tid);
+// Who synchronises between two gates of a tile: the whole CTA (hq_tile_kernel: one tile per CTA at a time) or
+// one 256-thread consumer group through a named barrier (hq_ring_kernel: two groups per CTA, each on its own tile).
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct GroupSync {
+  int id;   // named barrier 1 + group
+  __device__ __forceinline__ void operator()() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(HQ_THREADS) : "memory");
+  }
+};
+
+// One out-of-line copy per kernel of the constant-bank FFMA2 gates (k = 1..3, with / without a target on
+// amplitude bit 0): the slot index is a run-time (CTA-uniform) value, so the matrix elements are fetched with
+// uniform constant loads at a register offset and there is one code copy, not one per slot.
+#ifndef HQ_FAST_TEMPLATED
+#define HQ_FAST_TEMPLATED 1   // 1: one code copy per slot, immediate constant-bank offsets; 0: run-time slot index
+#endif
+// (inlined on purpose: `ph` must stay the kernel's own __grid_constant__ parameter for its elements to be
+// constant-bank operands; behind a call it decays to a generic pointer and every element becomes an LD)
+template <int MAXK>
+__device__ __forceinline__ void gate_fast_slot(float4* tile, const HqGateDesc* g, const HqPassHeader& ph, uint32_t slot,
+                                               int Tu, int tid) {
+#if HQ_FAST_TEMPLATED
+  switch (slot) {
+    case 0: gate_fast_f32<0, MAXK>(tile, g, ph, 0u, Tu, tid); break;
+    case 1: gate_fast_f32<1, MAXK>(tile, g, ph, 1u, Tu, tid); break;
+    case 2: gate_fast_f32<2, MAXK>(tile, g, ph, 2u, Tu, tid); break;
+    case 3: gate_fast_f32<3, MAXK>(tile, g, ph, 3u, Tu, tid); break;
+    case 4: gate_fast_f32<4, MAXK>(tile, g, ph, 4u, Tu, tid); break;
+    case 5: gate_fast_f32<5, MAXK>(tile, g, ph, 5u, Tu, tid); break;
+    case 6: gate_fast_f32<6, MAXK>(tile, g, ph, 6u, Tu, tid); break;
+    default: gate_fast_f32<7, MAXK>(tile, g, ph, 7u, Tu, tid); break;
+  }
+#else
+  gate_fast_f32<-1, MAXK>(tile, g, ph, slot, Tu, tid);
+#endif
+}
+template <int MAXK>
+__device__ __forceinline__ void gate_fast_slot(double2*, const HqGateDesc*, const HqPassHeader&, uint32_t, int, int) {}
+
+// Every gate of the pass on one tile held in shared memory; `sync` separates consecutive gates and is also
+// called after the last one (the drain reads what other threads wrote).
+// FAST: the kernel variant carries the constant-bank FFMA2 slots (complex64, passes whose gates all have k <= 3);
+// other variants send flagged gates down the generic path (the planner stores their matrices in the program too).
+template <typename T, int KCLASS, bool FAST, class Sync>
+__device__ __forceinline__ void apply_pass_gates(typename Traits<T>::Unit* tile, const HqGateDesc* gates,
+                                                 const HqPassHeader& ph, const unsigned char* prog, int Tbits, int Tu,
+                                                 int tid, const Sync& sync) {
+  typedef typename Traits<T>::Cplx Cplx;
+  const int V = Traits<T>::V;
+  const int MAXK = KCLASS == 0 ? 2 : (KCLASS == 1 ? 3 : 4);
+  const int MMAK = KCLASS == 3 ? HQ_MMA_MAX_K : MAXK;
+  const uint32_t n_gates = ph.n_gates;
+  for (uint32_t gi = 0; gi < n_gates; ++gi) {
+    const HqGateDesc* g = gates + gi;
+    if (FAST && V == 1 && KCLASS <= 1 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
+      gate_fast_slot<MAXK>(tile, g, ph, gi, Tu, tid);       // complex64 k <= 3: constant-bank FFMA2
+      sync();
+      continue;
     }
-    __syncthreads();
+    const uint32_t k = __ldg(&g->k);
+    const uint32_t mat_off = __ldg(&g->mat_off);
+    const uint32_t kind = __ldg(&g->kind);
+    if (KCLASS < 3 || kind != HQ_GATE_BIG) {
+      gate_small_generic<MAXK, MMAK>(tile, g, k, kind, prog, mat_off, Tu, tid);
+    } else {
+      const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + mat_off);
+      const int rounds = big_rounds(Tbits, int(k));
+      for (int r = 0; r < rounds; ++r) {
+        BigAcc<T> acc;
+        gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile), *g, Ut, Tbits, tid, r, acc);
+        sync();
+        gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile), *g, acc);
+      }
+    }
+    sync();
   }
 }
-
-template <typename T, int MAXK>
-__device__ __forceinline__ void fast_slots(float4* tile, const HqGateDesc* gates, const HqPassHeader& ph,
-                                           const unsigned char* prog, uint32_t n_gates, int Tu, int tid) {
-  fast_slot<0, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<1, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<2, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<3, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<4, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<5, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<6, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-  fast_slot<7, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-}
-template <typename T, int MAXK>
-__device__ __forceinline__ void fast_slots(double2*, const HqGateDesc*, const HqPassHeader&, const unsigned char*,
-                                           uint32_t, int, int) {}
 
 template <typename T, int KCLASS, int NBUF>
 __global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 && Traits<T>::V == 1) ? HQ_K0F_BLOCKS
                                 : ((KCLASS == 1 && Traits<T>::V == 0) ? HQ_K1D_BLOCKS
-                                   : ((KCLASS == 0 || (KCLASS == 1 && Traits<T>::V == 1)) ? 3 : 2))))
+                                   : ((KCLASS == 1 && Traits<T>::V == 1) ? HQ_K1F_BLOCKS : (KCLASS == 0 ? 3 : 2)))))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
                const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles) {
   typedef typename Traits<T>::Unit Unit;
   typedef typename Traits<T>::Cplx Cplx;
   const int V = Traits<T>::V;
-  const int MAXK = KCLASS == 0 ? 2 : (KCLASS == 1 ? 3 : 4);
-  const int MMAK = KCLASS == 3 ? HQ_MMA_MAX_K : MAXK;
   extern __shared__ __align__(16) unsigned char smem[];
 
   const int tid = threadIdx.x;
@@ -249,7 +300,6 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
   const int Tu = Tbits - V;
   const int Lu = Tbits - h - V;
   const uint32_t n_units = 1u << Tu;
-  const uint32_t n_gates = ph.n_gates;
   const int npt = Tu > HQ_THREADS_LOG2 ? (1 << (Tu - HQ_THREADS_LOG2)) : (uint32_t(tid) < n_units ? 1 : 0);
 
   Unit* bufs = reinterpret_cast<Unit*>(smem);
@@ -284,31 +334,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     }
     __syncthreads();
 
-    uint32_t gi0 = 0;
-    if (V == 1 && KCLASS <= 1 && ph.fast_mask) {
-      // unrolled slots: constant-bank matrices for the k = 2 gates, generic code for the others
-      gi0 = n_gates < HQ_FAST_SLOTS ? n_gates : HQ_FAST_SLOTS;
-      fast_slots<T, MAXK>(tile, gates, ph, prog, n_gates, Tu, tid);
-    }
-    for (uint32_t gi = gi0; gi < n_gates; ++gi) {
-      const HqGateDesc* g = gates + gi;
-      const uint32_t k = __ldg(&g->k);
-      const uint32_t mat_off = __ldg(&g->mat_off);
-      const uint32_t kind = __ldg(&g->kind);
-      if (KCLASS < 3 || kind != HQ_GATE_BIG) {
-        gate_small_generic<MAXK, MMAK>(tile, g, k, kind, prog, mat_off, Tu, tid);
-      } else {
-        const Cplx* Ut = reinterpret_cast<const Cplx*>(prog + mat_off);
-        const int rounds = big_rounds(Tbits, int(k));
-        for (int r = 0; r < rounds; ++r) {
-          BigAcc<T> acc;
-          gate_big_phaseA<T>(reinterpret_cast<const Cplx*>(tile), *g, Ut, Tbits, tid, r, acc);
-          __syncthreads();
-          gate_big_phaseB<T>(reinterpret_cast<Cplx*>(tile), *g, acc);
-        }
-      }
-      __syncthreads();
-    }
+    apply_pass_gates<T, KCLASS, (NBUF == 1)>(tile, gates, ph, prog, Tbits, Tu, tid, CtaSync());
 
     // drain
     if (!ph.has_perm) {
@@ -445,6 +471,261 @@ int launch_tile_pass(int dtype, void* state, unsigned n_qubits, const unsigned c
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return dtype == HQ_DTYPE_C64 ? launch_tile_pass_t<float>(state, n_qubits, prog, ph, s, grid_override)
                                : launch_tile_pass_t<double>(state, n_qubits, prog, ph, s, grid_override);
+}
+
+// ---------------------------------------------------------------------------------------
+// the ring kernel: the same pass as hq_tile_kernel, software-pipelined inside ONE persistent CTA per SM
+//
+//   warps  0 ..  7   consumer group 0   (256 threads each: exactly the thread count the gate code and the lane
+//   warps  8 .. 15   consumer group 1    tables of HqGateDesc are written for)
+//
+// Shared memory is a ring of HQ_RING_STAGES = 3 tile buffers.  Tile i of the CTA lives in stage i % 3 and is
+// processed by group i % 2: the group waits on the stage's `full` mbarrier, applies every gate of the pass with
+// named barriers between gates, streams the result back to HBM straight from shared memory, and then -- the
+// stage being free again -- issues the 16-byte cp.async copies (LDGSTS: no registers, arbitrary swizzled slots)
+// of tile i + 3 into it; their completion is signalled on `full` by cp.async.mbarrier.arrive.noinc, one arrival
+// per thread of the group.  So at any time two tiles are being computed on while a third is in flight from HBM
+// and the drain stores of the previous ones are still retiring: a group never waits for its own fill, the fill
+// it issues is consumed by the OTHER group half a tile time later.  (A first version had a 17th warp as a
+// dedicated producer and `empty` mbarriers; 17 warps cap the kernel at 96 registers -- five warps share one
+// sub-partition's register file -- which the k = 3 FFMA2 slots do not fit in.)
+//
+// XCHG: the drain writes to OTHER buffers -- dst[D] is the buffer (local or a peer GPU's, mapped over NVLink)
+// that receives the amplitudes whose local index bits xg.pos[] spell D, stored at the same local index with
+// those bits replaced by this rank's own digit: a rank-bit <-> local-bit exchange fused into the last pass
+// before it (hybridq_b200/dist.py), no separate permutation pass, no staging copy.
+// ---------------------------------------------------------------------------------------
+#define HQ_RING_STAGES 3
+#define HQ_RING_GROUPS 2
+#define HQ_RING_THREADS (HQ_RING_GROUPS * HQ_THREADS)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+// every cp.async this thread has issued so far arrives on `bar` when it has landed (no pending-count increment:
+// the arrival was budgeted at mbar_init)
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// Wait for the phase with the given parity to complete.  A protocol bug would spin forever and hang the GPU;
+// after ~2^26 failed probes (seconds) the kernel traps instead, which surfaces as a launch failure.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done && spins > (1u << 26)) __trap();
+  }
+}
+
+struct HqXchg {            // exchange redirect of the drain (all zero = plain in-place pass)
+  uint32_t s;              // number of local index bits swapped with rank bits (0 .. 3)
+  uint32_t mine;           // this rank's digit (value of the rank bits being swapped), deposited at pos[]
+  uint8_t pos[4];          // local AMPLITUDE-bit positions leaving the shard (>= V)
+  uint32_t reserved;
+  void* dst[8];            // destination buffer of digit D (dst[mine] is this rank's own second buffer)
+};
+
+template <typename T, int KCLASS, bool XCHG>
+__global__ void __launch_bounds__(HQ_RING_THREADS, 1)
+hq_ring_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
+               const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles,
+               const __grid_constant__ HqXchg xg) {
+  typedef typename Traits<T>::Unit Unit;
+  typedef typename Traits<T>::Cplx Cplx;
+  const int V = Traits<T>::V;
+  extern __shared__ __align__(16) unsigned char smem[];
+
+  const int Tbits = int(ph.tile_bits);
+  const int h = int(ph.n_high);
+  const int Tu = Tbits - V;
+  const int Lu = Tbits - h - V;
+  const int npt = 1 << (Tu - HQ_THREADS_LOG2);               // the launcher guarantees Tu >= HQ_THREADS_LOG2
+  Unit* const bufs = reinterpret_cast<Unit*>(smem);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + (size_t(16 * HQ_RING_STAGES) << Tu));
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < HQ_RING_STAGES; ++st) mbar_init(&full[st], HQ_THREADS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const unsigned long long first = blockIdx.x;
+  const unsigned long long count = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0ull;
+  // broadcast from lane 0 so that the compiler knows the group is warp-uniform (uniform-register operands)
+  const int group = __shfl_sync(0xffffffffu, int(threadIdx.x >> HQ_THREADS_LOG2), 0);
+  const int tid = threadIdx.x & (HQ_THREADS - 1);
+  const GroupSync sync{1 + group};
+  const HqGateDesc* gates = reinterpret_cast<const HqGateDesc*>(prog + ph.gates_off);
+  const uint64_t off_t = unit_offset(uint32_t(tid), Lu, V, ph.high_pos, h);
+  const uint32_t swz_t = swz(uint32_t(tid));
+  uint64_t xmask = 0, xmine = 0;
+  if (XCHG) {
+    for (uint32_t j = 0; j < xg.s; ++j) {
+      xmask |= uint64_t(1) << (xg.pos[j] - V);
+      xmine |= uint64_t((xg.mine >> j) & 1u) << (xg.pos[j] - V);
+    }
+  }
+
+  // this thread's share of the fill of the CTA's tile number i into its stage
+  auto issue_fill = [&](unsigned long long i) {
+    const int st = int(i % HQ_RING_STAGES);
+    const unsigned long long t = first + i * gridDim.x;
+    tile_fill<T>(bufs + (size_t(st) << Tu), state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t, ph, swz_t, npt);
+    mbar_arrive_cp_async(&full[st]);
+  };
+  // prologue: tiles 0 and 2 are fetched by group 0, tile 1 by group 1
+  for (unsigned long long i = group; i < HQ_RING_STAGES && i < count; i += HQ_RING_GROUPS) issue_fill(i);
+
+  for (unsigned long long i = group; i < count; i += HQ_RING_GROUPS) {
+    const int st = int(i % HQ_RING_STAGES);
+    mbar_wait(&full[st], uint32_t((i / HQ_RING_STAGES) & 1ull));
+    Unit* tile = bufs + (size_t(st) << Tu);
+    const unsigned long long t = first + i * gridDim.x;
+    const uint64_t ubase = (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t;
+
+    if (ph.n_gates) apply_pass_gates<T, KCLASS, true>(tile, gates, ph, prog, Tbits, Tu, tid, sync);
+
+    // drain straight from shared memory
+    if (!ph.has_perm) {
+#pragma unroll 4
+      for (int it = 0; it < npt; ++it) {
+        const uint64_t u = ubase + ph.iter_off[it];
+        const Unit v = tile[swz_t ^ ph.iter_swz[it]];
+        if (XCHG) {
+          uint32_t D = 0;
+          for (uint32_t j = 0; j < xg.s; ++j) D |= uint32_t((u >> (xg.pos[j] - V)) & 1ull) << j;
+          st_stream(reinterpret_cast<Unit*>(xg.dst[D]) + ((u & ~xmask) | xmine), v);
+        } else {
+          st_stream(state + u, v);
+        }
+      }
+    } else {
+      const Cplx* amps = reinterpret_cast<const Cplx*>(tile);
+      for (int it = 0; it < npt; ++it) {
+        const uint32_t c = uint32_t(tid) + (uint32_t(it) << HQ_THREADS_LOG2);
+        Cplx o[1 << V];
+#pragma unroll
+        for (uint32_t e = 0; e < (1u << V); ++e) o[e] = amps[amp_slot<T>(perm_src((c << V) | e, ph.perm, Tbits))];
+        const uint64_t u = ubase + ph.iter_off[it];
+        if (XCHG) {
+          uint32_t D = 0;
+          for (uint32_t j = 0; j < xg.s; ++j) D |= uint32_t((u >> (xg.pos[j] - V)) & 1ull) << j;
+          st_stream(reinterpret_cast<Unit*>(xg.dst[D]) + ((u & ~xmask) | xmine), make_unit(o));
+        } else {
+          st_stream(state + u, make_unit(o));
+        }
+      }
+    }
+    if (i + HQ_RING_STAGES < count) {
+      sync();                       // every thread of the group has read its part of the stage
+      issue_fill(i + HQ_RING_STAGES);
+    }
+  }
+  // no cp.async is left in flight: every fill that was issued has been waited for by one of the groups
+}
+
+static int g_tune_ring = -1;         // -1 = auto (large states), 0 = never, 1 = whenever the tile allows it
+void set_ring(int mode) {
+  if (mode >= -1 && mode <= 1) g_tune_ring = mode;
+}
+
+size_t ring_smem_bytes(const HqPassHeader& ph, int dtype) {
+  const int V = dtype == HQ_DTYPE_C64 ? 1 : 0;
+  const int Tu = int(ph.tile_bits) - V;
+  return (size_t(16 * HQ_RING_STAGES) << Tu) + HQ_RING_STAGES * sizeof(uint64_t);
+}
+
+// can this pass run on the ring kernel?  (tile of at least one unit per consumer thread)
+static bool ring_eligible(const HqPassHeader& ph, int dtype, unsigned n_qubits, const DeviceInfo& di) {
+  const int V = dtype == HQ_DTYPE_C64 ? 1 : 0;
+  const int Tu = int(ph.tile_bits) - V;
+  if (Tu < HQ_THREADS_LOG2 || ph.tile_bits > n_qubits) return false;
+  return ring_smem_bytes(ph, dtype) <= size_t(di.max_smem_optin);
+}
+
+template <typename T, int KCLASS, bool XCHG>
+static int launch_ring_variant(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                               const HqXchg& xg, cudaStream_t stream, int grid_override, const DeviceInfo& di, int dev) {
+  static bool attr_set[64];
+  auto kern = hq_ring_kernel<T, KCLASS, XCHG>;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
+    if (e != cudaSuccess) return int(e);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return int(e);
+    attr_set[dev] = true;
+  }
+  const int dtype = Traits<T>::V == 1 ? HQ_DTYPE_C64 : HQ_DTYPE_C128;
+  const unsigned long long n_tiles = 1ull << (n_qubits - ph.tile_bits);
+  unsigned long long grid = (unsigned long long)di.sm_count;
+  if (grid_override > 0) grid = (unsigned long long)grid_override;
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<unsigned(grid), HQ_RING_THREADS, ring_smem_bytes(ph, dtype), stream>>>(
+      reinterpret_cast<typename Traits<T>::Unit*>(state), prog, ph, n_tiles, xg);
+  return int(cudaGetLastError());
+}
+
+template <typename T, bool XCHG>
+static int launch_ring_t(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                         const HqXchg& xg, cudaStream_t stream, int grid_override, const DeviceInfo& di, int dev) {
+  const int kclass = ph.max_k <= 2 ? 0 : (ph.max_k <= 3 ? 1 : (ph.max_k <= 4 ? 2 : 3));
+  switch (kclass) {
+    case 0: return launch_ring_variant<T, 0, XCHG>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+    case 1: return launch_ring_variant<T, 1, XCHG>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+    case 2: return launch_ring_variant<T, 2, XCHG>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+    default: return launch_ring_variant<T, 3, XCHG>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+  }
+}
+
+// The pass entry point: ring kernel for large states (or when forced), hq_tile_kernel otherwise.
+// xchg != nullptr (an exchange redirect, see HqXchg) always takes the ring kernel.
+int launch_pass(int dtype, void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                const HqXchgDesc* xchg, void* stream, int grid_override) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ph.tile_bits > n_qubits) return int(cudaErrorInvalidValue);
+  const bool can_ring = ring_eligible(ph, dtype, n_qubits, di);
+  HqXchg xg;
+  memset(&xg, 0, sizeof(xg));
+  if (xchg && xchg->s) {
+    if (!can_ring || xchg->s > 3) return int(cudaErrorInvalidValue);
+    const unsigned V = dtype == HQ_DTYPE_C64 ? 1u : 0u;
+    xg.s = xchg->s;
+    xg.mine = xchg->mine;
+    for (unsigned j = 0; j < xchg->s; ++j) {
+      if (xchg->pos[j] < V || xchg->pos[j] >= n_qubits) return int(cudaErrorInvalidValue);
+      xg.pos[j] = (uint8_t)xchg->pos[j];
+    }
+    for (unsigned d = 0; d < (1u << xchg->s); ++d) {
+      if (!xchg->dst[d]) return int(cudaErrorInvalidValue);
+      xg.dst[d] = xchg->dst[d];
+    }
+    return dtype == HQ_DTYPE_C64 ? launch_ring_t<float, true>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev)
+                                 : launch_ring_t<double, true>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev);
+  }
+  // auto: measured on B200 (profiles/r02/sweep_ring_b.jsonl) the ring kernel only wins on passes that are purely
+  // HBM-bound (one small gate: 2.61 vs 2.82 ms at n = 30) -- with two or more gates per pass the gate arithmetic
+  // saturates the shared-memory and FMA pipes and three independent CTAs per SM hide the fills just as well --
+  // so it is used for the exchange-redirect passes (above) and on request.
+  const bool use_ring = can_ring && g_tune_ring == 1;
+  if (use_ring)
+    return dtype == HQ_DTYPE_C64 ? launch_ring_t<float, false>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev)
+                                 : launch_ring_t<double, false>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev);
+  return launch_tile_pass(dtype, state, n_qubits, prog, ph, stream, grid_override);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -824,9 +1105,12 @@ int launch_vdot(int dtype, const void* a, const void* b, uint64_t n_amps, double
 // measurement support (device-native counterparts of the reference's FunctionalGates
 // /root/reference/hybridq/gate/measure.py:25-75 and gate/projection.py:25-68)
 // ---------------------------------------------------------------------------------------
+#define HQ_MARGINAL_SMEM_K 10   // outcomes up to 2^10 are accumulated in a shared-memory histogram first
 struct BitsParams {
-  unsigned char pos[HQ_MAX_K];   // index bit of outcome bit j
+  unsigned char pos[32];               // index bit of outcome bit j
   unsigned k;
+  unsigned long long cond_mask;        // only amplitudes with (i & cond_mask) == cond_value take part
+  unsigned long long cond_value;
 };
 
 __device__ __forceinline__ unsigned outcome_of(unsigned long long i, const BitsParams& p) {
@@ -836,24 +1120,29 @@ __device__ __forceinline__ unsigned outcome_of(unsigned long long i, const BitsP
 }
 
 // out[2 s], out[2 s + 1] += sum over amplitudes with outcome s of re^2, im^2 (global double atomics;
-// `out` must be zeroed).  A thread keeps a running sum and flushes it to the CTA's shared-memory
-// histogram only when its outcome changes, the CTA flushes once at the end.
-template <typename T>
+// `out` must be zeroed).  A thread keeps a running sum and flushes it only when its outcome changes:
+// SMEM = true (k <= HQ_MARGINAL_SMEM_K) to the CTA's shared-memory histogram, which the CTA flushes once at
+// the end; SMEM = false (any k <= 24) straight to the global histogram.
+template <typename T, bool SMEM>
 __global__ void __launch_bounds__(256) hq_marginal_kernel(const T* __restrict__ state, unsigned long long n_amps,
                                                           const BitsParams p, double* __restrict__ out) {
   extern __shared__ double hist[];
   const unsigned bins = 2u << p.k;
-  for (unsigned b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0.0;
-  __syncthreads();
+  if (SMEM) {
+    for (unsigned b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0.0;
+    __syncthreads();
+  }
+  double* acc = SMEM ? hist : out;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   double are = 0, aim = 0;
   unsigned cur = 0;
   bool have = false;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+    if ((i & p.cond_mask) != p.cond_value) continue;
     const unsigned s = outcome_of(i, p);
     if (have && s != cur) {
-      atomicAdd(&hist[2 * cur], are);
-      atomicAdd(&hist[2 * cur + 1], aim);
+      atomicAdd(&acc[2 * cur], are);
+      atomicAdd(&acc[2 * cur + 1], aim);
       are = aim = 0;
     }
     cur = s;
@@ -863,41 +1152,53 @@ __global__ void __launch_bounds__(256) hq_marginal_kernel(const T* __restrict__ 
     aim += im * im;
   }
   if (have) {
-    atomicAdd(&hist[2 * cur], are);
-    atomicAdd(&hist[2 * cur + 1], aim);
+    atomicAdd(&acc[2 * cur], are);
+    atomicAdd(&acc[2 * cur + 1], aim);
   }
-  __syncthreads();
-  for (unsigned b = threadIdx.x; b < bins; b += blockDim.x)
-    if (hist[b] != 0.0) atomicAdd(&out[b], hist[b]);
+  if (SMEM) {
+    __syncthreads();
+    for (unsigned b = threadIdx.x; b < bins; b += blockDim.x)
+      if (hist[b] != 0.0) atomicAdd(&out[b], hist[b]);
+  }
 }
 
-int launch_marginal(int dtype, const void* state, unsigned n_qubits, const unsigned* pos, unsigned k, double* out_dev,
-                    void* stream) {
+int launch_marginal(int dtype, const void* state, unsigned n_qubits, const unsigned* pos, unsigned k,
+                    uint64_t cond_mask, uint64_t cond_value, double* out_dev, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (k > HQ_MAX_K || k > n_qubits) return int(cudaErrorInvalidValue);
+  if (k > HQ_MARGINAL_MAX_K || k > n_qubits) return int(cudaErrorInvalidValue);
   BitsParams p;
   memset(&p, 0, sizeof(p));
   p.k = k;
+  p.cond_mask = cond_mask;
+  p.cond_value = cond_value;
   for (unsigned j = 0; j < k; ++j) {
     if (pos[j] >= n_qubits) return int(cudaErrorInvalidValue);
     p.pos[j] = (unsigned char)pos[j];
   }
   const unsigned long long n = 1ull << n_qubits;
-  const size_t smem = (size_t(2) << k) * sizeof(double);
-  if (dtype == HQ_DTYPE_C64)
-    hq_marginal_kernel<float><<<grid_for(n, 256), 256, smem, s>>>((const float*)state, n, p, out_dev);
-  else
-    hq_marginal_kernel<double><<<grid_for(n, 256), 256, smem, s>>>((const double*)state, n, p, out_dev);
+  if (k <= HQ_MARGINAL_SMEM_K) {
+    const size_t smem = (size_t(2) << k) * sizeof(double);
+    if (dtype == HQ_DTYPE_C64)
+      hq_marginal_kernel<float, true><<<grid_for(n, 256), 256, smem, s>>>((const float*)state, n, p, out_dev);
+    else
+      hq_marginal_kernel<double, true><<<grid_for(n, 256), 256, smem, s>>>((const double*)state, n, p, out_dev);
+  } else {
+    if (dtype == HQ_DTYPE_C64)
+      hq_marginal_kernel<float, false><<<grid_for(n, 256), 256, 0, s>>>((const float*)state, n, p, out_dev);
+    else
+      hq_marginal_kernel<double, false><<<grid_for(n, 256), 256, 0, s>>>((const double*)state, n, p, out_dev);
+  }
   return int(cudaGetLastError());
 }
 
-// amplitudes whose outcome differs from `outcome` become 0, the others are scaled plane-wise
+// amplitudes with (i & mask) != value become 0, the others are scaled plane-wise (any number of bits)
 template <typename T>
-__global__ void __launch_bounds__(256) hq_project_kernel(T* __restrict__ state, unsigned long long n_amps, const BitsParams p,
-                                                         unsigned outcome, T scale_re, T scale_im) {
+__global__ void __launch_bounds__(256) hq_project_kernel(T* __restrict__ state, unsigned long long n_amps,
+                                                         unsigned long long mask, unsigned long long value,
+                                                         T scale_re, T scale_im) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
-    const bool keep = outcome_of(i, p) == outcome;
+    const bool keep = (i & mask) == value;
     typename Traits<T>::Cplx v = reinterpret_cast<typename Traits<T>::Cplx*>(state)[i];
     v.x = keep ? v.x * scale_re : T(0);
     v.y = keep ? v.y * scale_im : T(0);
@@ -905,22 +1206,15 @@ __global__ void __launch_bounds__(256) hq_project_kernel(T* __restrict__ state, 
   }
 }
 
-int launch_project(int dtype, void* state, unsigned n_qubits, const unsigned* pos, unsigned k, unsigned outcome,
+int launch_project(int dtype, void* state, unsigned n_qubits, uint64_t mask, uint64_t value,
                    double scale_re, double scale_im, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (k > HQ_MAX_K || k > n_qubits || outcome >= (1u << k)) return int(cudaErrorInvalidValue);
-  BitsParams p;
-  memset(&p, 0, sizeof(p));
-  p.k = k;
-  for (unsigned j = 0; j < k; ++j) {
-    if (pos[j] >= n_qubits) return int(cudaErrorInvalidValue);
-    p.pos[j] = (unsigned char)pos[j];
-  }
+  if (n_qubits < 64 && ((mask >> n_qubits) || (value & ~mask))) return int(cudaErrorInvalidValue);
   const unsigned long long n = 1ull << n_qubits;
   if (dtype == HQ_DTYPE_C64)
-    hq_project_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((float*)state, n, p, outcome, float(scale_re), float(scale_im));
+    hq_project_kernel<float><<<grid_for(n, 256), 256, 0, s>>>((float*)state, n, mask, value, float(scale_re), float(scale_im));
   else
-    hq_project_kernel<double><<<grid_for(n, 256), 256, 0, s>>>((double*)state, n, p, outcome, scale_re, scale_im);
+    hq_project_kernel<double><<<grid_for(n, 256), 256, 0, s>>>((double*)state, n, mask, value, scale_re, scale_im);
   return int(cudaGetLastError());
 }
 

@@ -26,6 +26,21 @@ size_t tile_pass_smem_bytes(const HqPassHeader& ph, int dtype, int nbuf);
 // ctas_per_sm: cap on resident CTAs per SM (0 = occupancy limit)
 void set_tuning(int nbuf, int ctas_per_sm);
 
+// Exchange redirect of a pass's write-back (multi-GPU, hybridq_b200/dist.py): the amplitudes whose LOCAL index bits
+// pos[0..s) spell the digit D are written to buffer dst[D] -- this GPU's second buffer for D == mine, a peer GPU's
+// (mapped over NVLink) otherwise -- at the same local index with those bits replaced by `mine`.
+struct HqXchgDesc {
+  unsigned s;
+  unsigned mine;
+  unsigned pos[4];
+  void* dst[8];
+};
+// One pass over the state: the pipelined ring kernel (hq_ring_kernel) for large states, hq_tile_kernel otherwise.
+// xchg may be null.  ring mode: -1 auto, 0 never, 1 whenever the tile allows it (tests).
+int launch_pass(int dtype, void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                const HqXchgDesc* xchg, void* stream, int grid_override);
+void set_ring(int mode);
+
 // Direct (no shared memory) single-gate kernel for k <= 3 with every target at or above
 // amplitude bit `V` (see hq_kernels.cu); U is read from kernel parameters.
 int launch_direct_gate(int dtype, void* state, unsigned n_qubits, const void* U_host,
@@ -54,11 +69,13 @@ int launch_vdot(int dtype, const void* a, const void* b, uint64_t n_amps, double
                 unsigned n_partial, void* stream);
 
 // out_dev[2 s], out_dev[2 s + 1] += sum of re^2, im^2 over the amplitudes whose index bits pos[0..k) spell the
-// outcome s (bit j of s = index bit pos[j]); out_dev holds 2 * 2^k doubles and must be zeroed (measure.py:25-50)
+// outcome s (bit j of s = index bit pos[j]) and whose index satisfies (i & cond_mask) == cond_value; out_dev holds
+// 2 * 2^k doubles and must be zeroed; k <= HQ_MARGINAL_MAX_K (measure.py:25-50)
+#define HQ_MARGINAL_MAX_K 24
 int launch_marginal(int dtype, const void* state, unsigned n_qubits, const unsigned* pos, unsigned k,
-                    double* out_dev, void* stream);
-// projection onto one outcome with plane-wise scale factors (projection.py:25-68)
-int launch_project(int dtype, void* state, unsigned n_qubits, const unsigned* pos, unsigned k, unsigned outcome,
+                    uint64_t cond_mask, uint64_t cond_value, double* out_dev, void* stream);
+// projection onto the amplitudes with (index & mask) == value, plane-wise scale factors (projection.py:25-68)
+int launch_project(int dtype, void* state, unsigned n_qubits, uint64_t mask, uint64_t value,
                    double scale_re, double scale_im, void* stream);
 
 }  // namespace hq

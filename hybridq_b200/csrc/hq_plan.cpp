@@ -12,12 +12,18 @@ namespace hq {
 int default_tile_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 13 : 12; }
 int default_min_run_bits(int dtype) { return dtype == HQ_DTYPE_C64 ? 5 : 5; }
 int default_merge_max_k(int) { return 2; }
-// Measured on B200 (profiles/r01/microbench_mma_b.jsonl): the tensor-core path beats the FMA
-// paths for every k >= 3 (complex64) and k >= 2 (complex128).
-int default_mma_min_k(int dtype) { return dtype == HQ_DTYPE_C64 ? 3 : 2; }
+// complex128: FP64 mma.sync (exact IEEE accumulation) beats the DFMA paths for every k >= 2 (profiles/r01).
+// complex64: k <= 3 runs on the constant-bank FFMA2 slots -- the reference's own fp32 FMA arithmetic, no norm
+// drift (3xTF32 on mma.sync is ~15 % faster at k = 3 but its truncating accumulator loses 4e-5 of norm^2 per 600
+// gates); k >= 4, where the tile really is a dense contraction (16x16 complex and up) and
+// the FMA path is 2-7x slower, goes to the tensor cores.  PlanOptions.mma_min_k overrides (0 = never, 3 = r01).
+int default_mma_min_k(int dtype) { return dtype == HQ_DTYPE_C64 ? 4 : 2; }
 
 namespace {
 
+#ifndef HQ_MERGE_SLACK
+#define HQ_MERGE_SLACK 10
+#endif
 const int kMaxGatesPerPass = 48;   // gate-applies per pass before merging
 
 int vbits(int dtype) { return dtype == HQ_DTYPE_C64 ? 1 : 0; }
@@ -380,7 +386,9 @@ int union_k(uint64_t a, uint64_t b) { return __builtin_popcountll(a | b); }
 // paths (constant-bank FFMA2 slots for complex64 k = 2, row pairs for complex128) and the tensor-core
 // path (3xTF32 / FP64 mma.sync).  Only the ratios matter.
 int measured_cost(int dtype, bool mma_on, int mma_min_k, int k) {
-  static const int c64_fma[5] = {0, 660, 665, 2180, 5280}, c64_mma[5] = {0, 660, 940, 1255, 2420};
+  // complex64 FMA column, round 2: k <= 3 are the constant-bank FFMA2 slots (gate_stream_f32; k = 3 measured at
+  // 1.36 ms per matrix at n = 30, profiles/r02/sweep_ring_b.jsonl), k = 4 the generic register path
+  static const int c64_fma[5] = {0, 600, 620, 1360, 5280}, c64_mma[5] = {0, 600, 940, 1255, 2420};
   static const int c128_fma[5] = {0, 620, 1255, 2650, 7190}, c128_mma[5] = {0, 620, 720, 1160, 2320};
   if (k < 1) return 0;
   if (k > 4) return 1 << 30;
@@ -404,7 +412,10 @@ std::vector<Cluster> merge_pass(const std::vector<Canon>& canon, const std::vect
       for (int c = int(cl.size()) - 1; c >= 0; --c) {
         const int ku = union_k(cl[size_t(c)].mask, gm);
         if (ku <= max_k && ku <= HQ_SMALL_K) {
-          const int gain = cost(int(cl[size_t(c)].gate.k)) + cost(int(g.k)) - cost(ku);
+          // a merged matrix that costs up to HQ_MERGE_SLACK % more than its two parts is still taken: the merge
+          // is pairwise and greedy, and a cluster that has grown to k bits absorbs every later gate on those
+          // bits for free (a triangle of k = 2 gates becomes ONE k = 3 matrix only if the first pair may merge)
+          const int gain = cost(int(cl[size_t(c)].gate.k)) + cost(int(g.k)) - cost(ku) + cost(ku) * HQ_MERGE_SLACK / 100;
           // prefer the cluster that shares bits with g (later ones are disjoint by construction)
           if (gain >= 0 && gain > best_gain) {
             best_gain = gain;
@@ -544,8 +555,8 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         if (lb < 0) { plan.error = "internal: target bit outside tile"; return 1; }
         gl.tpos[i] = uint8_t(lb);
       }
-      // a lone k <= 2 gate keeps its plain matrix: such passes go to the direct kernel (hq_abi.cu)
-      const bool lone_small = merged[d].size() == 1 && c.k <= 2;
+      // a lone k <= 3 gate keeps its plain matrix: such passes go to the direct kernel (hq_abi.cu)
+      const bool lone_small = merged[d].size() == 1 && c.k <= 3;
       gl.mma = mma_on && !lone_small && int(c.k) >= mma_min_k && int(c.k) <= HQ_MMA_MAX_K &&
                mma_layout(gl.tpos, int(c.k), Tbits, V, gl.L);
       gl.bytes = gl.mma ? mma_frag_bytes(c.k) : (((esz << (2 * c.k)) + 15) & ~size_t(15));
@@ -608,10 +619,11 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         write_matrix<double>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
       mat_cursor += gl.bytes;
       ++gate_cursor;
-      if (dtype == HQ_DTYPE_C64 && gd.kind == HQ_GATE_SMALL && opts.fast_slots != 0 && ci < HQ_FAST_SLOTS && c.k == 2 &&
-          gd.tpos[0] != 0) {
+      if (dtype == HQ_DTYPE_C64 && gd.kind == HQ_GATE_SMALL && opts.fast_slots != 0 && ci < HQ_FAST_SLOTS &&
+          c.k <= HQ_FAST_MAX_K && Tbits - int(c.k) >= 1) {
         pi.header.fast_mask |= 1u << ci;
-        for (size_t e = 0; e < 16; ++e) {
+        pi.header.fast_k[ci] = uint8_t(c.k | (gd.tpos[0] == 0 ? 4u : 0u));
+        for (size_t e = 0; e < (size_t(1) << (2 * c.k)); ++e) {
           pi.header.fast_u[ci][2 * e] = float(c.U[e].real());
           pi.header.fast_u[ci][2 * e + 1] = float(c.U[e].imag());
         }
@@ -622,6 +634,14 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     plan.passes.push_back(std::move(pi));
   }
   return 0;
+}
+
+void make_identity_pass(int dtype, unsigned n, HqPassHeader& ph) {
+  const int V = vbits(dtype);
+  int T = std::min(default_tile_bits(dtype), max_tile_bits(dtype));
+  T = std::min<int>(T, int(n));
+  make_tile({}, T, T, n, ph);      // one contiguous run of 2^T amplitudes, no high bits
+  make_iter_tables(ph, V);
 }
 
 int plan_build_bitperm(Plan& plan, int dtype, unsigned n, const std::vector<unsigned>& perm_full,

@@ -74,4 +74,8 @@ int plan_build(Plan& plan, int dtype, unsigned n_qubits, const std::vector<GateI
 int plan_build_bitperm(Plan& plan, int dtype, unsigned n_qubits, const std::vector<unsigned>& perm_full,
                        const PlanOptions& opts);
 
+// Header of a pass that applies no gate and no permutation (a plain copy of the state through the tile kernel):
+// the carrier of an exchange redirect when no local pass precedes the exchange (hq_plan_run_range_xchg).
+void make_identity_pass(int dtype, unsigned n_qubits, HqPassHeader& ph);
+
 }  // namespace hq

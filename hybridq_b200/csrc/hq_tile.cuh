@@ -245,44 +245,99 @@ HQ_DEV void ffma2_bcast(F2& acc, const F2& x, float s) {
 #endif
 }
 
-template <int S>
-HQ_DEV void gate_fast_f32_k2(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph,
-                             int Tu, int tid) {
-  const int nq = Tu - 2;
+// Streaming FFMA2 gate (complex64 fast slots): the 2^K x 2^K matrix sits in the pass header, i.e. in the constant
+// bank, so every matrix element reaches the FMA pipe as a uniform-register operand (SASS: FFMA2 R, R.F32x2,
+// UR.F32, R.F32x2) and costs no register and no shared-memory traffic.  The thread walks the COLUMNS of the
+// matrix: one 16-byte shared load brings the two amplitudes of a unit, which are multiplied into all 2^K row
+// accumulators at once (32 independent FFMA2 per column for K = 3) -- so only the accumulators (2^K pairs per
+// group) and one column of inputs are live, whatever K is: 20 registers of state for K = 2, 36 for K = 3.
+// The accumulation order per output amplitude is j ascending with re*re, -im*im / re*im, im*re interleaved,
+// the order of the reference's scalar loop (U.h:93-94) up to fp32 FMA contraction.
+//   KK   number of UNIT-level target bits (tbl_x has 2^KK entries)
+//   LOW  false: no target on amplitude bit 0: K = KK, the even and the odd amplitude of a unit belong to two
+//               different groups, the thread updates both;
+//        true : matrix bit 0 is amplitude bit 0: K = KK + 1, a unit holds columns 2j, 2j + 1 of ONE group.
+//   S    slot index when it is known at compile time (every matrix element is then a constant-bank operand at
+//        an immediate offset), -1 = use the run-time `slot`
+template <int KK, bool LOW, int S>
+HQ_DEV void gate_stream_f32(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph, uint32_t slot,
+                            int Tu, int tid) {
+  const int UD = 1 << KK;                    // units per work item
+  const int DIM = LOW ? 2 * UD : UD;         // matrix dimension
+  const int nq = Tu - KK;
   const uint32_t nwork = 1u << nq;
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
   const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
   const IterBasis ib = load_iter_basis(g->tbl_iter);
-  uint32_t xo[4];
+  uint32_t xo[UD];
   HQ_UNROLL
-  for (int m = 0; m < 4; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
+  for (int m = 0; m < UD; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
+  // matrix element e of the slot: straight out of the constant bank (row-major, (re, im) interleaved)
+#define HQ_FAST_U(e) (S >= 0 ? ph.fast_u[S >= 0 ? S : 0][e] : ph.fast_u[slot][e])
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
     const uint32_t sb = st ^ iter_offset(ib, it);
-    // amplitude pairs (re, im) of the even / odd group and the same multiplied by i: (-im, re)
-    F2 e[4], o[4], ie[4], io[4];
-    HQ_UNROLL
-    for (int m = 0; m < 4; ++m) {
-      const float4 v = tile[sb ^ xo[m]];
-      e[m].lo = v.x;   e[m].hi = v.y;
-      o[m].lo = v.z;   o[m].hi = v.w;
-      ie[m].lo = -v.y; ie[m].hi = v.x;
-      io[m].lo = -v.w; io[m].hi = v.z;
-    }
-    HQ_UNROLL
-    for (int i = 0; i < 4; ++i) {
-      F2 a0 = {0.f, 0.f}, a1 = {0.f, 0.f};
+    if (!LOW) {
+      F2 ae[DIM], ao[DIM];
       HQ_UNROLL
-      for (int j = 0; j < 4; ++j) {
-        const float ur = ph.fast_u[S][2 * (i * 4 + j)], ui = ph.fast_u[S][2 * (i * 4 + j) + 1];
-        ffma2_bcast(a0, e[j], ur);      // (ar, ai) += ur * (xr, xi)
-        ffma2_bcast(a0, ie[j], ui);     // (ar, ai) += ui * (-xi, xr)
-        ffma2_bcast(a1, o[j], ur);
-        ffma2_bcast(a1, io[j], ui);
+      for (int i = 0; i < DIM; ++i) { ae[i].lo = ae[i].hi = 0.f; ao[i].lo = ao[i].hi = 0.f; }
+      HQ_UNROLL
+      for (int j = 0; j < DIM; ++j) {
+        const float4 v = tile[sb ^ xo[j]];
+        const F2 e = {v.x, v.y}, ie = {-v.y, v.x}, o = {v.z, v.w}, io = {-v.w, v.z};
+        HQ_UNROLL
+        for (int i = 0; i < DIM; ++i) {
+          const float ur = HQ_FAST_U(2 * (i * DIM + j)), ui = HQ_FAST_U(2 * (i * DIM + j) + 1);
+          ffma2_bcast(ae[i], e, ur);       // (ar, ai) += ur * (xr, xi)
+          ffma2_bcast(ae[i], ie, ui);      // (ar, ai) += ui * (-xi, xr)
+          ffma2_bcast(ao[i], o, ur);
+          ffma2_bcast(ao[i], io, ui);
+        }
       }
-      tile[sb ^ xo[i]] = make_float4(a0.lo, a0.hi, a1.lo, a1.hi);
+      HQ_UNROLL
+      for (int i = 0; i < DIM; ++i) tile[sb ^ xo[i]] = make_float4(ae[i].lo, ae[i].hi, ao[i].lo, ao[i].hi);
+    } else {
+      F2 a[DIM];
+      HQ_UNROLL
+      for (int i = 0; i < DIM; ++i) a[i].lo = a[i].hi = 0.f;
+      HQ_UNROLL
+      for (int ju = 0; ju < UD; ++ju) {
+        const float4 v = tile[sb ^ xo[ju]];
+        const F2 e = {v.x, v.y}, ie = {-v.y, v.x}, o = {v.z, v.w}, io = {-v.w, v.z};
+        HQ_UNROLL
+        for (int i = 0; i < DIM; ++i) {
+          const float ur0 = HQ_FAST_U(2 * (i * DIM + 2 * ju)), ui0 = HQ_FAST_U(2 * (i * DIM + 2 * ju) + 1);
+          const float ur1 = HQ_FAST_U(2 * (i * DIM + 2 * ju + 1)), ui1 = HQ_FAST_U(2 * (i * DIM + 2 * ju + 1) + 1);
+          ffma2_bcast(a[i], e, ur0);
+          ffma2_bcast(a[i], ie, ui0);
+          ffma2_bcast(a[i], o, ur1);
+          ffma2_bcast(a[i], io, ui1);
+        }
+      }
+      HQ_UNROLL
+      for (int iu = 0; iu < UD; ++iu)
+        tile[sb ^ xo[iu]] = make_float4(a[2 * iu].lo, a[2 * iu].hi, a[2 * iu + 1].lo, a[2 * iu + 1].hi);
     }
+  }
+}
+
+#undef HQ_FAST_U
+
+// one fast slot: k = ph.fast_k[slot] in 1..3, low = matrix bit 0 on amplitude bit 0
+template <int S, int MAXK>
+HQ_DEV void gate_fast_f32(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph, uint32_t slot,
+                          int Tu, int tid) {
+  const uint32_t k = ph.fast_k[slot] & 3u;
+  const bool low = (ph.fast_k[slot] & 4u) != 0;
+  if (!low) {
+    if (k == 2) gate_stream_f32<2, false, S>(tile, g, ph, slot, Tu, tid);
+    else if (k == 3) { if (MAXK >= 3) gate_stream_f32<3, false, S>(tile, g, ph, slot, Tu, tid); }
+    else gate_stream_f32<1, false, S>(tile, g, ph, slot, Tu, tid);
+  } else {
+    if (k == 2) gate_stream_f32<1, true, S>(tile, g, ph, slot, Tu, tid);
+    else if (k == 3) { if (MAXK >= 3) gate_stream_f32<2, true, S>(tile, g, ph, slot, Tu, tid); }
+    else gate_stream_f32<0, true, S>(tile, g, ph, slot, Tu, tid);
   }
 }
 

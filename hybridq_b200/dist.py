@@ -51,6 +51,13 @@ class Op:
 def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
     """Turn [(U, logical positions)] into a list of Ops for p = 2^g ranks."""
     nl = n - g
+    if nl < 1:
+        raise ValueError(f"cannot shard a {n}-qubit state over 2^{g} ranks: no local qubits left")
+    kmax = max((len(p) for _, p in lowered), default=0)
+    if kmax > nl:
+        # every target of a gate must be a local bit at the same time
+        raise ValueError(f"a gate acts on {kmax} qubits but each of the 2^{g} ranks holds only {nl} local qubits; "
+                         "use fewer ranks (or shard=False)")
     where = list(range(n))                      # logical bit -> physical bit (>= nl: rank bit)
     ops: list[Op] = []
     pending = list(range(len(lowered)))
@@ -80,7 +87,12 @@ def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
                 first_use.setdefault(b, idx)
         # farthest next use first; ties: keep current rank bits, then higher logical bits
         order = sorted(range(n), key=lambda b: (-first_use.get(b, math.inf), where[b] < nl, -b))
+        before = list(where)
         emit_remap_ordered(ops, stats, where, n, nl, order[:g])
+        if where == before:
+            raise RuntimeError("sharded schedule made no progress (internal error): "
+                               f"pending gate on bits {lowered[pending[0]][1]}, rank bits "
+                               f"{[b for b in range(n) if where[b] >= nl]}")
 
     if restore and g > 0:
         for _ in range(2):

@@ -122,8 +122,11 @@ def simulate(circuit,
     kwargs.setdefault("plan_options", None)
     kwargs.setdefault("device", None)
     kwargs.setdefault("out", None)           # optional (e.g. pinned) complex array receiving the result
-    kwargs.setdefault("shard", "auto")       # True / False / 'auto': shard the state over the ranks of an
-                                             # initialised torch.distributed process group (one GPU per rank)
+    kwargs.setdefault("shard", False)        # True: shard the state over the ranks of an initialised
+                                             # torch.distributed process group (one GPU per rank) -- a collective
+                                             # call that returns this rank's shard; 'auto': shard when such a group
+                                             # exists and the circuit fits the shards, else run unsharded.  The
+                                             # default is the reference's behaviour: the full state on every caller.
 
     hq = _try_hybridq()
     is_ref_circuit = False
@@ -228,6 +231,11 @@ def simulate(circuit,
     t_pre = time.perf_counter() - t_pre
 
     dist = _dist_if_sharded(kwargs["shard"])
+    if dist is not None and kwargs["shard"] == "auto":
+        g_bits = int(round(np.log2(dist.get_world_size())))
+        kmax = max((len(p) for kind, seg in segments if kind == "gates" for _, p in seg), default=0)
+        if n_qubits - g_bits < max(kmax, 12):        # too small to be worth (or able to be) sharded
+            dist = None
     if dist is not None:
         kwargs["_qmap"] = qmap
         return _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwargs, t_pre)
@@ -315,8 +323,8 @@ def _dist_if_sharded(shard):
 
 def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwargs, t_pre):
     """Multi-GPU evolution (hybridq_b200.dist): every rank calls simulate() with the same circuit; an
-    array initial state is the FULL state on every rank (each uploads its own slice) or, if it has
-    2^(n - log2 p) amplitudes, this rank's shard.  Returns this rank's shard of the final state
+    array initial state is the FULL state on every rank (each uploads its own slice).  Returns this rank's shard
+    of the final state
     (amplitudes [rank * 2^(n-g), (rank+1) * 2^(n-g)) in canonical order).  The reference has no
     counterpart (simulation.py:379-380)."""
     from .dist import ShardedRunner
@@ -334,10 +342,7 @@ def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwa
         runner.init_product(initial_state)
     else:
         flat = np.asarray(initial_state).reshape(-1)
-        if flat.size == 2 ** n_qubits:
-            flat = flat[runner.rank * 2 ** nl:(runner.rank + 1) * 2 ** nl]
-        elif flat.size != 2 ** nl:
-            raise ValueError("Wrong number of qubits for initial/final state.")
+        flat = flat[runner.rank * 2 ** nl:(runner.rank + 1) * 2 ** nl]
         runner.load_shard(np.ascontiguousarray(flat, dtype=complex_type))
     runner.engine.sync()
     t_up = time.perf_counter() - t_up
@@ -370,9 +375,10 @@ _PROJECTION_ATOL = 1e-6      # hybridq/gate/projection.py:31
 
 
 def _apply_projection(gate, state: DeviceState, qmap: dict, renormalize: bool = True) -> None:
-    """ProjectionGate on the device.  Follows the reference on split planes (projection.py:70-116 with
-    _Projection :25-68 on each plane): a plane whose projected norm is <= 1e-6 is zeroed as a whole, then
-    the state is renormalised by what is left."""
+    """ProjectionGate on the device, any number of qubits.  Follows the reference on split planes
+    (projection.py:70-116 with _Projection :25-68 on each plane): a plane whose projected norm is <= 1e-6 is
+    zeroed as a whole, then the state is renormalised by what is left.  Only the one outcome's re^2 / im^2 sums
+    are needed, so the reduction is a conditional sum (no 2^k histogram)."""
     spec = tuple(gate.state)
     if len(spec) != len(tuple(gate.qubits)):
         raise ValueError("'state' is not consistent with 'axes'.")
@@ -380,7 +386,12 @@ def _apply_projection(gate, state: DeviceState, qmap: dict, renormalize: bool = 
         raise ValueError("Only projections to the z-basis are supported at the moment.")
     pos = [qmap[q] for q in gate.qubits]
     outcome = sum(int(b) << j for j, b in enumerate(spec))
-    sums = state.marginal(pos)[outcome]
+    if hasattr(state, "broadcast_int"):                 # sharded state (hybridq_b200.dist.ShardedRunner)
+        sums = state.marginal(pos)[outcome]
+    else:
+        mask = sum(1 << p for p in pos)
+        value = sum(int(b) << p for p, b in zip(pos, spec))
+        sums = state.marginal([], cond_mask=mask, cond_value=value)[0]
     keep = [float(np.sqrt(x) > _PROJECTION_ATOL) for x in sums]
     scale = 1.0
     if renormalize:
@@ -390,27 +401,54 @@ def _apply_projection(gate, state: DeviceState, qmap: dict, renormalize: bool = 
     state.project(pos, outcome, keep[0] * scale, keep[1] * scale)
 
 
+_MEASURE_CHUNK = 20          # outcome bits per reduction when more than 24 qubits are measured at once
+
+
 def _apply_measure(gate, state: DeviceState, qmap: dict, renormalize: bool = True) -> int:
     """MeasureGate on the device (measure.py:25-75): outcome probabilities by a device reduction, the draw
-    with numpy's global generator exactly as the reference does (`np.random.choice(size, p=probs)`, :52),
-    projection + renormalisation by a second kernel.  Outcome index: gate.qubits[0] is the most significant
-    digit (the reference transposes the measured axes to the front in gate.qubits order, :39-43)."""
+    with numpy's global generator exactly as the reference does (`np.random.choice(size, p=probs)`, :52 -- the
+    probabilities are handed over as they are, in the state's real precision, so an unnormalised state is
+    rejected by numpy here as it is there), projection + renormalisation by a second kernel.  Outcome index:
+    gate.qubits[0] is the most significant digit (the reference transposes the measured axes to the front in
+    gate.qubits order, :39-43).
+
+    Up to 24 qubits the draw is the reference's own (same generator state -> same outcome).  Beyond that the
+    2^k probability vector the reference builds on the host does not fit anywhere sensible, so the outcome is
+    drawn digit group by digit group (most significant first, `_MEASURE_CHUNK` bits at a time, each from the
+    marginal conditioned on the groups already drawn): the same distribution, a different use of the
+    generator."""
     qubits = tuple(gate.qubits)
     k = len(qubits)
     pos = [qmap[q] for q in reversed(qubits)]           # outcome bit j <-> qubits[k-1-j]
-    sums = state.marginal(pos)
-    probs = sums.sum(axis=1)
-    # numpy.random.choice normalises its cdf itself (cdf /= cdf[-1]) but first rejects a p that is off 1 by
-    # more than sqrt(eps); normalising here leaves the draw unchanged and keeps deep complex64 circuits,
-    # whose norm drifts by a few 1e-5 per thousand gates on the tensor-core path, from tripping that check
-    probs = (probs / probs.sum()).astype(np.float32 if state.complex_type == np.complex64 else np.float64)
-    if hasattr(state, "broadcast_int"):                 # sharded state: rank 0 draws for everybody
-        outcome = state.broadcast_int(int(np.random.choice(2 ** k, p=probs)) if state.rank == 0 else 0)
+    ft = np.float32 if state.complex_type == np.complex64 else np.float64
+    sharded = hasattr(state, "broadcast_int")
+    if k <= 24 or sharded:
+        sums = state.marginal(pos)
+        probs = sums.sum(axis=1).astype(ft)
+        if sharded:                                     # rank 0 draws for everybody
+            outcome = state.broadcast_int(int(np.random.choice(2 ** k, p=probs)) if state.rank == 0 else 0)
+        else:
+            outcome = int(np.random.choice(2 ** k, p=probs))
+        p_outcome = float(sums[outcome].sum())
     else:
-        outcome = int(np.random.choice(2 ** k, p=probs))
+        outcome, mask, value, p_prev = 0, 0, 0, 1.0
+        hi = k
+        while hi > 0:
+            lo = max(0, hi - _MEASURE_CHUNK)
+            chunk = pos[lo:hi]
+            sums = state.marginal(chunk, cond_mask=mask, cond_value=value).sum(axis=1)
+            probs = sums / sums.sum()
+            s = int(np.random.choice(len(probs), p=probs))
+            outcome |= s << lo
+            for j, p in enumerate(chunk):
+                mask |= 1 << p
+                value |= ((s >> j) & 1) << p
+            p_prev = float(sums[s])
+            hi = lo
+        p_outcome = p_prev
     scale = 1.0
     if renormalize:
-        scale = 1.0 / float(np.sqrt(sums[outcome].sum()))
+        scale = 1.0 / float(np.sqrt(p_outcome))
     state.project(pos, outcome, scale, scale)
     return outcome
 

@@ -9,6 +9,7 @@ and makes its final ``to_complex`` pass (:669-675) unnecessary.
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Sequence
 
 import numpy as np
@@ -17,15 +18,37 @@ from . import _lib
 from ._lib import lib, check, PlanOptions
 
 
-def _stream_handle(stream=None) -> ctypes.c_void_p:
+def _stream_handle(stream=None, device=None) -> ctypes.c_void_p:
+    """Raw cudaStream_t of `stream`, or of torch's current stream ON `device` (not on whatever device happens to
+    be current: the C ABI launches on the calling thread's current device, see `_on`)."""
     import torch
-    s = torch.cuda.current_stream() if stream is None else stream
+    s = torch.cuda.current_stream(device) if stream is None else stream
     return ctypes.c_void_p(s.cuda_stream)
+
+
+def _on(device):
+    """Context manager making `device` the calling thread's current CUDA device for the duration of a C-ABI
+    call: every hq_* entry point launches on cudaGetDevice()'s device, so a state that lives on another GPU
+    than the current one must switch first (kernels ran in the wrong context otherwise)."""
+    import torch
+    return torch.cuda.device(device)
 
 
 def _torch_ctype(complex_type):
     import torch
     return torch.complex64 if np.dtype(complex_type) == np.complex64 else torch.complex128
+
+
+def _dev(method):
+    """Run a DeviceState method with the state's device current (see `_on`)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with _on(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
+MARGINAL_MAX_K = 24      # HQ_MARGINAL_MAX_K: outcome bits per hq_marginal_cond_dev call
 
 
 class Plan:
@@ -81,12 +104,13 @@ class Plan:
     def run(self, state: "DeviceState", first: int | None = None, last: int | None = None, stream=None):
         if state.n_qubits != self.n_qubits or state.dtype != self.dtype:
             raise ValueError("plan and state disagree on size or precision")
-        if first is None and last is None:
-            check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream)), "hq_plan_run")
-        else:
-            check(lib.hq_plan_run_range(self._h, state.ptr, first or 0,
-                                        self.n_passes if last is None else last,
-                                        _stream_handle(stream)), "hq_plan_run_range")
+        with _on(state.device):
+            if first is None and last is None:
+                check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream, state.device)), "hq_plan_run")
+            else:
+                check(lib.hq_plan_run_range(self._h, state.ptr, first or 0,
+                                            self.n_passes if last is None else last,
+                                            _stream_handle(stream, state.device)), "hq_plan_run_range")
 
 
 class BitPermPlan:
@@ -116,7 +140,8 @@ class BitPermPlan:
     def run(self, state: "DeviceState", stream=None):
         if state.n_qubits != self.n_qubits or state.dtype != self.dtype:
             raise ValueError("plan and state disagree on size or precision")
-        check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream)), "hq_plan_run")
+        with _on(state.device):
+            check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream, state.device)), "hq_plan_run")
 
 
 class DeviceState:
@@ -143,80 +168,97 @@ class DeviceState:
         return ctypes.c_void_p(self.tensor.data_ptr())
 
     # -- transfers ------------------------------------------------------------------
+    @_dev
     def upload(self, psi: np.ndarray, stream=None, sync: bool = True) -> "DeviceState":
         psi = np.asarray(psi)
         if psi.size != self.n_amps:
             raise ValueError("wrong number of amplitudes")
         if psi.dtype != self.complex_type or not psi.flags.c_contiguous:
             psi = np.ascontiguousarray(psi, dtype=self.complex_type)
-        s = _stream_handle(stream)
+        s = _stream_handle(stream, self.device)
         check(lib.hq_memcpy_h2d(self.ptr, ctypes.c_void_p(psi.ctypes.data), self.nbytes, s), "h2d")
         if sync:
             check(lib.hq_stream_sync(s), "sync")
         return self
 
+    @_dev
     def download(self, out: np.ndarray | None = None, stream=None) -> np.ndarray:
         if out is None:
             out = np.empty(self.n_amps, dtype=self.complex_type)
         if out.size != self.n_amps or out.dtype != self.complex_type or not out.flags.c_contiguous:
             raise ValueError("bad output array")
-        s = _stream_handle(stream)
+        s = _stream_handle(stream, self.device)
         check(lib.hq_memcpy_d2h(ctypes.c_void_p(out.ctypes.data), self.ptr, self.nbytes, s), "d2h")
         check(lib.hq_stream_sync(s), "sync")
         return out
 
+    @_dev
     def sync(self, stream=None) -> None:
-        check(lib.hq_stream_sync(_stream_handle(stream)), "sync")
+        check(lib.hq_stream_sync(_stream_handle(stream, self.device)), "sync")
 
     # -- preparation / reductions -----------------------------------------------------
+    @_dev
     def init_product(self, spec: str, stream=None) -> "DeviceState":
         if len(spec) == 1:
             spec = spec * self.n_qubits
         check(lib.hq_init_product_dev(self.ptr, self.dtype, self.n_qubits, spec.encode(),
-                                      _stream_handle(stream)), "hq_init_product_dev")
+                                      _stream_handle(stream, self.device)), "hq_init_product_dev")
         return self
 
+    @_dev
     def init_random(self, seed: int = 0, index_offset: int = 0, scale: float = 0.0, stream=None):
         check(lib.hq_init_random_dev(self.ptr, self.dtype, self.n_qubits, seed, index_offset, scale,
-                                     _stream_handle(stream)), "hq_init_random_dev")
+                                     _stream_handle(stream, self.device)), "hq_init_random_dev")
         return self
 
+    @_dev
     def norm2(self, stream=None) -> float:
         r = ctypes.c_double()
-        check(lib.hq_norm2_dev(self.ptr, self.dtype, self.n_amps, ctypes.byref(r), _stream_handle(stream)),
+        check(lib.hq_norm2_dev(self.ptr, self.dtype, self.n_amps, ctypes.byref(r), _stream_handle(stream, self.device)),
               "hq_norm2_dev")
         return r.value
 
+    @_dev
     def vdot(self, other: "DeviceState", stream=None) -> complex:
         """<self|other> = sum conj(self) * other."""
         r = (ctypes.c_double * 2)()
-        check(lib.hq_vdot_dev(self.ptr, other.ptr, self.dtype, self.n_amps, r, _stream_handle(stream)),
+        check(lib.hq_vdot_dev(self.ptr, other.ptr, self.dtype, self.n_amps, r, _stream_handle(stream, self.device)),
               "hq_vdot_dev")
         return complex(r[0], r[1])
 
-    def marginal(self, pos: Sequence[int], stream=None) -> np.ndarray:
+    @_dev
+    def marginal(self, pos: Sequence[int], stream=None, cond_mask: int = 0, cond_value: int = 0) -> np.ndarray:
         """(2^k, 2) array: sum of re^2 and of im^2 over the amplitudes whose index bits ``pos`` spell the
-        outcome s (bit j of s = index bit pos[j]).  ``.sum(axis=1)`` are the measurement probabilities of
-        the reference's ``_Measure(get_probs_only=True)`` (hybridq/gate/measure.py:25-50)."""
+        outcome s (bit j of s = index bit pos[j]), restricted to the indices with
+        ``(index & cond_mask) == cond_value``.  ``.sum(axis=1)`` are the measurement probabilities of
+        the reference's ``_Measure(get_probs_only=True)`` (hybridq/gate/measure.py:25-50).  k <= 24 per call."""
         pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        if len(pos) > MARGINAL_MAX_K:
+            raise ValueError(f"at most {MARGINAL_MAX_K} outcome bits per call (condition on earlier chunks)")
         out = np.zeros((2 ** len(pos), 2), dtype=np.float64)
-        check(lib.hq_marginal_dev(self.ptr, self.dtype, self.n_qubits,
-                                  pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos),
-                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _stream_handle(stream)),
-              "hq_marginal_dev")
+        check(lib.hq_marginal_cond_dev(self.ptr, self.dtype, self.n_qubits,
+                                       pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos),
+                                       int(cond_mask), int(cond_value),
+                                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                       _stream_handle(stream, self.device)), "hq_marginal_cond_dev")
         return out
 
+    @_dev
     def project(self, pos: Sequence[int], outcome: int, scale_re: float = 1.0, scale_im: float = 1.0, stream=None):
         """Zero every amplitude whose index bits ``pos`` do not spell ``outcome``; scale the others
         plane-wise (hybridq/gate/projection.py:25-68)."""
-        pos = np.ascontiguousarray(pos, dtype=np.uint32)
-        check(lib.hq_project_dev(self.ptr, self.dtype, self.n_qubits,
-                                 pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos), int(outcome),
-                                 float(scale_re), float(scale_im), _stream_handle(stream)), "hq_project_dev")
+        mask = value = 0
+        for j, p in enumerate(pos):
+            mask |= 1 << int(p)
+            value |= ((int(outcome) >> j) & 1) << int(p)
+        check(lib.hq_project_mask_dev(self.ptr, self.dtype, self.n_qubits, mask, value,
+                                      float(scale_re), float(scale_im), _stream_handle(stream, self.device)),
+              "hq_project_mask_dev")
         return self
 
+    @_dev
     def scale(self, factor: float, stream=None):
-        check(lib.hq_scale_dev(self.ptr, self.dtype, self.n_amps, float(factor), _stream_handle(stream)),
+        check(lib.hq_scale_dev(self.ptr, self.dtype, self.n_amps, float(factor), _stream_handle(stream, self.device)),
               "hq_scale_dev")
         return self
 
@@ -224,24 +266,27 @@ class DeviceState:
         return DeviceState(self.n_qubits, self.complex_type, self.device, tensor=self.tensor.clone())
 
     # -- gates -------------------------------------------------------------------------
+    @_dev
     def apply(self, U: np.ndarray, pos: Sequence[int], stream=None, direct: bool = False):
         """One gate-apply (hq_apply_U_dev): pos[i] = index bit of matrix bit i, any bits."""
         U = np.ascontiguousarray(U, dtype=self.complex_type)
         pos = np.ascontiguousarray(pos, dtype=np.uint32)
         fn = lib.hq_apply_U_direct_dev if direct else lib.hq_apply_U_dev
         check(fn(self.ptr, self.dtype, self.n_qubits, ctypes.c_void_p(U.ctypes.data),
-                 pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos), _stream_handle(stream)),
+                 pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos), _stream_handle(stream, self.device)),
               "hq_apply_U_dev")
         return self
 
+    @_dev
     def swap(self, pos: Sequence[int], stream=None):
         """In-place permutation of the low len(pos) index bits (hq_swap_dev)."""
         pos = np.ascontiguousarray(pos, dtype=np.uint32)
         check(lib.hq_swap_dev(self.ptr, self.dtype, self.n_qubits,
                               pos.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(pos),
-                              _stream_handle(stream)), "hq_swap_dev")
+                              _stream_handle(stream, self.device)), "hq_swap_dev")
         return self
 
+    @_dev
     def permute_bits(self, perm: Sequence[int], options: PlanOptions | None = None, stream=None):
         """new index bit i <- old index bit perm[i] for every i < n (in place)."""
         BitPermPlan(perm, self.n_qubits, self.complex_type, options).run(self, stream)

@@ -125,6 +125,16 @@ int hq_marginal_dev(const void* state, int dtype, unsigned int n_qubits, const u
                     unsigned int k, double* out_host, void* stream);
 int hq_project_dev(void* state, int dtype, unsigned int n_qubits, const unsigned int* pos, unsigned int k,
                    unsigned int outcome, double scale_re, double scale_im, void* stream);
+/* The same two operations without the k <= 10 limit of a shared-memory histogram (the reference's Measure /
+ * Projection accept any number of qubits, gate/measure.py:77, gate/projection.py:72):
+ * hq_marginal_cond_dev: as hq_marginal_dev for k <= 24 outcome bits, restricted to the amplitudes whose index
+ *   satisfies (index & cond_mask) == cond_value -- lets a caller sample more than 24 qubits chunk by chunk
+ *   (k = 0 gives the re^2 / im^2 sums of one outcome of any width: what Projection needs);
+ * hq_project_mask_dev: keep (and scale plane-wise) the amplitudes with (index & mask) == value, zero the rest. */
+int hq_marginal_cond_dev(const void* state, int dtype, unsigned int n_qubits, const unsigned int* pos,
+                         unsigned int k, uint64_t cond_mask, uint64_t cond_value, double* out_host, void* stream);
+int hq_project_mask_dev(void* state, int dtype, unsigned int n_qubits, uint64_t mask, uint64_t value,
+                        double scale_re, double scale_im, void* stream);
 
 /* ---- circuit plans: fuse a gate stream into tile passes once, run many times ---- */
 typedef struct hq_plan hq_plan;
@@ -172,12 +182,32 @@ int hq_plan_run(hq_plan* plan, void* state, void* stream);
 /* launch passes [first, last) only */
 int hq_plan_run_range(hq_plan* plan, void* state, int first, int last, void* stream);
 
+/* ---- multi-GPU: rank-bit <-> local-bit exchange fused into a pass (no reference counterpart: the reference's
+ * evolution path refuses MPI, hybridq/circuit/simulation/simulation.py:379-380) ----
+ * hq_plan_run_range_xchg runs passes [first, last) like hq_plan_run_range, but the LAST pass writes its result
+ * to other buffers instead of back in place: the amplitudes whose LOCAL index bits pos[0..s) (s <= 3, amplitude-bit
+ * positions) spell the digit D go to dst[D] -- this GPU's second shard buffer for D == mine, a peer GPU's buffer
+ * opened with hq_ipc_open otherwise (stores travel over NVLink) -- at the same local index with those bits
+ * replaced by the digit `mine`.  After every rank has run it (and a barrier), rank r's second buffer holds the
+ * shard with rank bits and local bits pos[] swapped.  s = 0 is hq_plan_run_range.
+ * hq_ipc_*: cudaIpc plumbing for the peer buffers (handle = 64 bytes, exchanged by the host code). */
+int hq_plan_run_range_xchg(hq_plan* plan, void* state, int first, int last, unsigned int s, unsigned int mine,
+                           const unsigned int* pos, void* const* dst, void* stream);
+int hq_ipc_get_handle(void* dptr, void* handle_out_64);
+int hq_ipc_open(const void* handle_64, void** dptr);
+int hq_ipc_close(void* dptr);
+
 /* measurement knobs of the tile kernel: nbuf = 0 (auto, default: prefetch the next tile while the
  * current one is processed whenever the second buffer costs no resident CTA), 1 (single-buffered)
  * or 2 (always double-buffered); ctas_per_sm = cap on resident CTAs per SM (0 = occupancy limit);
- * use_direct = 1 (default): a pass holding one k <= 2 gate runs on the shared-memory-free kernel.
+ * use_direct = 1 (default): a pass holding one k <= 3 gate runs on the shared-memory-free kernel.
  * Negative values leave a knob unchanged. */
 int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct);
+/* which kernel runs a pass: -1 (default) / 0 = the tile kernel (three independent CTAs per SM), except for the
+ * exchange-redirect passes of hq_plan_run_range_xchg, which always run on the pipelined ring kernel (one
+ * persistent CTA per SM, a 3-stage shared-memory ring fed by cp.async + mbarrier, two consumer groups);
+ * 1 = the ring kernel for every pass whose tile has >= 256 units (measurements, tests). */
+int hq_set_ring(int mode);
 
 /* counters: kernels launched by this library in this process since the last reset */
 uint64_t hq_launch_count(void);

@@ -21,6 +21,7 @@ oracle or CUDA path):
   functional.npz   `simulate(optimize='evolution')` on circuits with Projection and Measure FunctionalGates
                  (simulation.py:525-554, gate/projection.py, gate/measure.py), numpy's generator seeded.
   expectation.npz  `hybridq.circuit.simulation.expectation_value` (simulation.py:1125) on 12-qubit states.
+  dm_large.npz   the same at 10 and 12 qubits (2^20 / 2^24 superkets): lowered gates + sampled amplitudes.
   dm.npz         `hybridq.dm.circuit.simulation.simulate` (dm/circuit/simulation.py:118) on a
                  6-qubit circuit with depolarizing noise; the lowered 12-"qubit" circuit that
                  it hands to `simulate` is captured and stored as (matrix, qubit-index) lists.
@@ -398,8 +399,64 @@ def make_expectation():
     np.savez_compressed(HERE / "expectation.npz", **out)
     print("expectation.npz:", idx, "cases", [complex(out[f"e{i}_value"]) for i in range(idx)])
 
+# ---------------------------------------------------------------- dm_large.npz (config 5 parity at 2^20 / 2^24)
+def make_dm_large():
+    """SURVEY 8(d) config 5 parity: 10- and 12-qubit density matrices (2^20 / 2^24 superkets, complex64) through the
+    reference's dm front-end and its evolution core.  The full output is too large to commit, so the file holds
+    the lowered gate list (what dm.simulate hands to `simulate`), 8192 sampled amplitudes of the reference result,
+    its trace and its squared norm; the GPU test recomputes the full vector with the reference core
+    (oracle/_ref) on the box and additionally checks these samples."""
+    import hybridq.dm.circuit.simulation as dmsim
+    import hybridq.circuit.simulation as csim
+    from hybridq.gate import MatrixGate
+    from hybridq.circuit import Circuit, utils as cutils
+    from hybridq.noise.utils import add_depolarizing_noise
+
+    captured = {}
+    real_simulate = csim.simulate
+
+    def spy(circuit, initial_state, **kw):
+        captured["circuit"] = list(circuit)
+        captured["initial_state"] = initial_state
+        return real_simulate(circuit=circuit, initial_state=initial_state, **kw)
+
+    out = {"n_cases": np.int32(2)}
+    for ci, nq in enumerate((10, 12)):
+        gates = matching_circuit(nq, depth=6, seed=5000 + nq)
+        circ = Circuit(MatrixGate(g.U, qubits=list(g.qubits)) for g in gates)
+        noisy = add_depolarizing_noise(circ, probs=(0.001, 0.01))
+        csim.simulate = spy
+        try:
+            rho = dmsim.simulate(noisy, initial_state="0", optimize="evolution", simplify=False, compress=0,
+                                 complex_type="complex64")
+        finally:
+            csim.simulate = real_simulate
+        lowered = list(cutils.flatten(Circuit(captured["circuit"])))
+        qubits = sorted({q for g in lowered for q in g.qubits})
+        assert len(qubits) == 2 * nq
+        flat = np.asarray(rho).reshape(-1)
+        rng = np.random.default_rng(77 + nq)
+        idx = np.unique(np.concatenate([rng.integers(0, flat.size, 8192),
+                                        np.arange(2 ** nq, dtype=np.int64) * (2 ** nq + 1)]))   # incl. the diagonal
+        out[f"L{ci}_nq"] = np.int32(nq)
+        out[f"L{ci}_ngates"] = np.int32(len(lowered))
+        for j, g in enumerate(lowered):
+            out[f"L{ci}_g{j}_U"] = np.asarray(g.matrix()).astype(np.complex64)
+            out[f"L{ci}_g{j}_q"] = np.array([qubits.index(q) for q in g.qubits], dtype=np.int32)
+        out[f"L{ci}_init"] = np.array(captured["initial_state"])
+        out[f"L{ci}_idx"] = idx.astype(np.int64)
+        out[f"L{ci}_val"] = flat[idx]
+        out[f"L{ci}_trace"] = np.complex128(np.trace(np.asarray(rho).reshape(2 ** nq, 2 ** nq)))
+        out[f"L{ci}_norm2"] = np.float64(np.vdot(flat.astype(np.complex128), flat.astype(np.complex128)).real)
+        print(f"dm_large nq={nq}: {len(lowered)} lowered gates, trace = {out[f'L{ci}_trace']:.6f}, "
+              f"k-hist = {np.bincount([len(g.qubits) for g in lowered])}")
+    np.savez_compressed(HERE / "dm_large.npz", **out)
+
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dm_large":
+        make_dm_large()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dm15":
         make_dm15()
         sys.exit(0)
@@ -415,6 +472,7 @@ if __name__ == "__main__":
     make_dot_transpose()
     make_dm()
     make_dm15()
+    make_dm_large()
     make_expectation()
     make_functional()
     for f in sorted(HERE.glob("*.npz")):

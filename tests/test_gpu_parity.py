@@ -345,3 +345,71 @@ def test_full_size_round_trip_and_norm(hb, n, ctype):
     import torch
     err = float((st.tensor - ref.tensor).abs().max())
     assert err <= TOL[ctype], err
+
+
+# ------------------------------------------------------------------ wide Measure / Projection
+def test_measure_and_projection_on_more_than_ten_qubits(hb, oracle):
+    """The reference's Measure / Projection take any number of qubits (gate/measure.py:77, gate/projection.py:72);
+    measuring every qubit is the usual sampling idiom.  k = 14 > 10 goes through the global-memory histogram and
+    reproduces the reference's draw (same numpy generator state); k = 12 projection through the conditional sum."""
+    from hybridq_b200.circuits import matching_circuit, to_positions, MeasureApply, ProjectionApply, random_state
+    n = 14
+    gates = matching_circuit(n, depth=3, seed=14)
+    lowered, _ = to_positions(gates, qubits=list(range(n)))
+    for ctype in ("complex64", "complex128"):
+        psi0 = random_state(n, ctype, seed=2)
+        mid = oracle.evolve_oracle(psi0, [(U.astype(ctype), p) for U, p in lowered])
+        # Measure over all qubits, given in a scrambled order
+        order = [int(x) for x in np.random.default_rng(5).permutation(n)]
+        np.random.seed(1234)
+        want, s = oracle.numpy_measure(mid, [n - 1 - q for q in order])
+        np.random.seed(1234)
+        out = hb.simulate(gates + [MeasureApply(tuple(order))], initial_state=psi0.reshape((2,) * n), complex_type=ctype)
+        assert np.abs(out.reshape(-1) - want).max() <= TOL[ctype]
+        assert np.count_nonzero(out) == 1
+        # Projection of 12 of the 14 qubits
+        qs = order[:12]
+        bits = "".join(str((i * 7 + 3) % 2) for i in range(12))
+        want = oracle.numpy_project(mid, [n - 1 - q for q in qs], [int(b) for b in bits])
+        out = hb.simulate(gates + [ProjectionApply(tuple(qs), bits)], initial_state=psi0.reshape((2,) * n), complex_type=ctype)
+        assert np.abs(out.reshape(-1) - want).max() <= 4 * TOL[ctype]
+
+
+def test_measure_more_than_24_qubits_samples_in_chunks(hb):
+    """26 measured qubits: the outcome is drawn group by group from conditional marginals; the result must be
+    the basis state of the drawn outcome, and over a product state with known single-qubit probabilities the
+    drawn bits must be the certain ones."""
+    from hybridq_b200.circuits import MeasureApply, GateApply
+    n = 26
+    spec = "01" * 13                                   # qubit q (label q = string position) is |0> or |1>
+    H = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    np.random.seed(7)
+    circ = [GateApply(H, (3,)), GateApply(H, (20,)), MeasureApply(tuple(range(n)))]
+    st = hb.simulate(circ, initial_state=spec, complex_type="complex64", return_numpy_array=False)
+    assert abs(st.norm2() - 1) < 1e-6
+    out = st.download()
+    idx = np.flatnonzero(out)
+    assert idx.size == 1 and abs(abs(out[idx[0]]) - 1) < 1e-6
+    bits = format(int(idx[0]), f"0{n}b")               # string position q <-> qubit label q (MSB first)
+    for q in range(n):
+        if q not in (3, 20):
+            assert bits[q] == spec[q], q
+
+
+def test_state_on_a_device_that_is_not_current(hb, oracle, c_oracle):
+    """DeviceState(device=1) while cuda:0 is current must launch on cuda:1."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hybridq_b200.circuits import matching_circuit, to_positions, random_state
+    n = 16
+    lowered, _ = to_positions(matching_circuit(n, depth=4, seed=1), qubits=list(range(n)))
+    psi0 = random_state(n, "complex64", seed=3)
+    ref = oracle.evolve_oracle(psi0, [(U.astype("complex64"), p) for U, p in lowered], c_oracle)
+    torch.cuda.set_device(0)
+    st = hb.DeviceState(n, "complex64", device=1).upload(psi0)
+    hb.Plan(lowered, n, "complex64").run(st)
+    assert st.tensor.device.index == 1 and torch.cuda.current_device() == 0
+    assert np.abs(st.download() - ref).max() <= TOL["complex64"]
+    out = hb.simulate(matching_circuit(n, depth=4, seed=1), initial_state=psi0.reshape((2,) * n), device=1)
+    assert np.abs(out.reshape(-1) - ref).max() <= TOL["complex64"]

@@ -89,9 +89,11 @@ def test_lane_mapping_is_bank_conflict_free():
 
 
 def test_merging_follows_the_measured_cost_table():
-    """In-pass merging (hq_plan.cpp measured_cost): with the tensor-core path two k = 2 gates sharing a bit
-    become one k = 3 matrix, disjoint k = 2 gates stay apart (a k = 4 matrix costs more than two k = 2 ones),
-    a 1-qubit gate is absorbed by a neighbour; with FMA paths only nothing grows beyond k = 2."""
+    """In-pass merging (hq_plan.cpp measured_cost).  complex128 (tensor-core path from k = 2): two k = 2 gates
+    sharing a bit become one k = 3 matrix.  complex64 (FFMA2 slots up to k = 3, measured 0.62 / 1.36 ms): the same
+    (1.36 vs 1.24 is within the 10 % slack the greedy merge grants, because the k = 3 cluster then absorbs every
+    later gate on its bits: a triangle of three k = 2 gates becomes one matrix).  Always: disjoint k = 2 gates stay
+    apart, a 1-qubit gate is absorbed by a neighbour."""
     from helpers import Emu
     emu = Emu()
     n = 14
@@ -102,6 +104,21 @@ def test_merging_follows_the_measured_cost_table():
         assert mats([[3, 5], [7, 8]]) == 2                      # disjoint -> two matrices
         assert mats([[3, 5], [5]]) == 1 and mats([[4], [4, 9]]) == 1
         assert mats([[3, 5], [5, 8], [8, 3]]) == 1              # triangle on 3 bits -> one k = 3
-        assert mats([[3, 5], [5, 8]], (0, -1, 1, 0, 0, -1, -1, 1, 0)) == 2      # FMA only: no k = 3 merge
+        assert mats([[3, 5], [5, 8]], (0, -1, 1, 0, 0, -1, -1, 1, 0)) == 2      # FMA only: no k = 3 merge of a chain
         assert mats([[3, 5], [5, 8]], (0, -1, 1, 0, 0, 0, -1, 1, -1)) == 2      # merging off
         assert mats([[1, 2, 3], [2, 3, 4]]) == 1                # two k = 3 sharing two bits -> k = 4
+
+
+def test_plan_sharded_rejects_gates_wider_than_a_shard():
+    """plan_sharded() used to loop forever when a gate touched more qubits than a rank holds."""
+    import numpy as np
+    import pytest
+    from hybridq_b200.dist import plan_sharded
+    with pytest.raises(ValueError):
+        plan_sharded([(np.eye(8), [0, 1, 2])], n=5, g=3)
+    with pytest.raises(ValueError):
+        plan_sharded([(np.eye(8), [0, 1, 2])], n=4, g=2)
+    with pytest.raises(ValueError):
+        plan_sharded([(np.eye(2), [0])], n=2, g=2)
+    ops, stats, where = plan_sharded([(np.eye(8), [0, 1, 4])], n=5, g=2)     # k = n - g: just fits
+    assert stats["exchanges"] >= 1 and where == list(range(5))

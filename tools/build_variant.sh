@@ -8,7 +8,7 @@ name=$1; shift
 out=hybridq_b200/lib/variants; obj=$out/obj_$name
 mkdir -p $obj
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ --expt-relaxed-constexpr -Xptxas -v"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ --expt-relaxed-constexpr -Xptxas -v -split-compile 0"
 for f in hq_kernels hq_abi; do
   $NVCC $FLAGS "$@" -c hybridq_b200/csrc/$f.cu -o $obj/$f.o 2> $obj/$f.ptxas.log || (cat $obj/$f.ptxas.log; exit 1)
 done
