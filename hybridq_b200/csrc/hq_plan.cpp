@@ -538,6 +538,25 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
   for (size_t d = 0; d < drafts.size(); ++d) {
     merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost, dtype, mma_on, mma_min_k);
+    if (merge_pass_cost < 0 && merge_max_k > 2) {
+      // second look at every cluster that grew beyond k = 2 on the strength of the slack: keep it only if it
+      // really is cheaper than the same gates merged no further than k = 2 (a chain of two k = 2 gates is not, a
+      // triangle of three is)
+      std::vector<Cluster> refined;
+      for (Cluster& c : merged[d]) {
+        if (c.gate.k > 2 && c.ids.size() > 1) {
+          std::vector<Cluster> sub = merge_pass(canon, c.ids, 2, merge_pass_cost, dtype, mma_on, mma_min_k);
+          long split = 0;
+          for (const Cluster& sc : sub) split += measured_cost(dtype, mma_on, mma_min_k, int(sc.gate.k));
+          if (split < measured_cost(dtype, mma_on, mma_min_k, int(c.gate.k))) {
+            for (Cluster& sc : sub) refined.push_back(std::move(sc));
+            continue;
+          }
+        }
+        refined.push_back(std::move(c));
+      }
+      merged[d].swap(refined);
+    }
     total_gates += merged[d].size();
     // single gates may use shorter runs than the fuser is allowed to create
     const int L = choose_run_bits(drafts[d].bits, T, drafts[d].ids.size() > 1 ? fuse_min_run : hard_min_run);

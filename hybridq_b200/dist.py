@@ -12,13 +12,23 @@ Schedule (computed identically on every rank, pure Python, no communication):
 
   local     run every pending gate whose targets are all local bits (skipping over blocked
             gates when they commute, like the fuser) as fused tile passes;
-  remap     choose the new set of g rank bits = the logical bits whose next use is farthest
-            away (Belady), move the bits that must become rank bits to the top of the local
-            index with one in-place bit-permutation pass, then EXCHANGE: every rank swaps
-            (2^s - 1)/2^s of its shard with the 2^s - 1 ranks that differ in the s rank bits
-            being replaced (grouped NCCL send/recv into the second buffer, ping-pong);
-  restore   at the end of the circuit put every logical bit back in place (<= 2 exchanges
-            + one local permutation), so the result is in canonical order.
+  exchange  choose the new set of g rank bits = the logical bits whose next use is farthest
+            away (Belady) among those that sit at a local position >= MIN_XPOS, and SWAP the s
+            rank bits that must come in with the s local positions of the bits that go out --
+            in place, wherever those positions are: no permutation pass moves them to the top
+            first.  Every rank ships (2^s - 1)/2^s of its shard to the 2^s - 1 ranks that differ
+            in the swapped rank bits.
+  restore   at the end of the circuit put every logical bit back in place (<= 3 exchanges
+            + one local permutation pass), so the result is in canonical order.
+
+How an exchange moves data (round 2): FUSED into the write-back of the local pass that precedes
+it.  Every rank maps its peers' second shard buffer over NVLink (cudaIpc through the C ABI) and the
+last tile pass before the exchange streams each finished tile straight from shared memory to
+where it belongs -- the own second buffer or a peer's (hq_plan_run_range_xchg, hq_ring_kernel<XCHG>)
+-- so the NVLink traffic overlaps the gate arithmetic of the same pass tile by tile; one tiny
+all-reduce afterwards is the cross-rank barrier, then the buffers swap roles.  (Round 1: a
+permutation pass, then grouped NCCL send/recv of contiguous chunks, serialised with the kernels:
+`exchange_sendrecv` below is still the path of engines without peer mapping -- the CPU tests.)
 
 The local work is delegated to an *engine*; the product engine is :class:`CudaEngine`
 (hand-written kernels through the C ABI).  The CPU-only tests inject an oracle-backed
@@ -33,22 +43,26 @@ from typing import Sequence
 
 import numpy as np
 
+MIN_XPOS = 8          # lowest local bit position that may be swapped with a rank bit: the pieces that cross
+                      # NVLink are contiguous runs of 2^MIN_XPOS amplitudes (2 KiB complex64)
+
 
 # ------------------------------------------------------------------------------------------
 # schedule
 # ------------------------------------------------------------------------------------------
 class Op:
-    __slots__ = ("kind", "gates", "gate_ids", "perm", "gbits", "moved_frac")
+    __slots__ = ("kind", "gates", "gate_ids", "perm", "gbits", "lpos")
 
-    def __init__(self, kind, gates=None, gate_ids=None, perm=None, gbits=None):
+    def __init__(self, kind, gates=None, gate_ids=None, perm=None, gbits=None, lpos=None):
         self.kind = kind            # 'local' | 'permute' | 'exchange'
         self.gates = gates          # [(U, physical positions)]
         self.gate_ids = gate_ids
         self.perm = perm            # local bit permutation: new bit i <- old bit perm[i]
-        self.gbits = gbits          # rank-bit indices (0..g-1) swapped with the top local bits
+        self.gbits = gbits          # exchange: rank-bit indices (0..g-1) ...
+        self.lpos = lpos            # ... swapped one to one with these local bit positions
 
 
-def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
+def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True, min_xpos: int | None = None):
     """Turn [(U, logical positions)] into a list of Ops for p = 2^g ranks."""
     nl = n - g
     if nl < 1:
@@ -58,6 +72,8 @@ def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
         # every target of a gate must be a local bit at the same time
         raise ValueError(f"a gate acts on {kmax} qubits but each of the 2^{g} ranks holds only {nl} local qubits; "
                          "use fewer ranks (or shard=False)")
+    xmin = MIN_XPOS if min_xpos is None else min_xpos
+    xmin = max(0, min(xmin, nl - g - kmax))       # small shards: fall back to lower positions
     where = list(range(n))                      # logical bit -> physical bit (>= nl: rank bit)
     ops: list[Op] = []
     pending = list(range(len(lowered)))
@@ -85,28 +101,38 @@ def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
         for idx, gi in enumerate(pending):
             for b in lowered[gi][1]:
                 first_use.setdefault(b, idx)
-        # farthest next use first; ties: keep current rank bits, then higher logical bits
-        order = sorted(range(n), key=lambda b: (-first_use.get(b, math.inf), where[b] < nl, -b))
+        need_now = set(lowered[pending[0]][1])
+        # candidates for being a rank bit: the current ones, and local bits high enough to be swapped out;
+        # farthest next use first; ties: the bits whose home is a rank position (so that the final restore
+        # finds them in place), then the current rank bits, then higher physical positions
+        cands = [b for b in range(n) if b not in need_now and (where[b] >= nl or where[b] >= xmin)]
+        order = sorted(cands, key=lambda b: (-first_use.get(b, math.inf), b < nl, where[b] < nl, -where[b]))
         before = list(where)
-        emit_remap_ordered(ops, stats, where, n, nl, order[:g])
+        emit_exchange(ops, stats, where, n, nl, order[:g])
         if where == before:
             raise RuntimeError("sharded schedule made no progress (internal error): "
                                f"pending gate on bits {lowered[pending[0]][1]}, rank bits "
                                f"{[b for b in range(n) if where[b] >= nl]}")
 
     if restore and g > 0:
-        for _ in range(2):
-            cur_global = [b for b in range(n) if where[b] >= nl]
-            if all(where[b] == b for b in cur_global):
+        for _ in range(3):
+            inv = {where[b]: b for b in range(n)}
+            wrong_pos = [pos for pos in range(nl, n) if inv[pos] != pos]      # rank positions with a wrong occupant
+            if not wrong_pos:
                 break
-            # keep the correctly placed rank bits; vacated positions receive their own logical bit
-            # when it is local now, otherwise any low logical bit (the second round fixes those)
-            new_global = [b for b in cur_global if where[b] == b]
-            need = g - len(new_global)
-            cands = [b for b in range(nl, n) if where[b] < nl][:need]
-            fill = [b for b in range(nl) if where[b] < nl]
-            new_global += cands + fill[:need - len(cands)]
-            emit_remap_ordered(ops, stats, where, n, nl, new_global)
+            # a wrong occupant is swapped with its position's rightful bit when that one is local now, otherwise
+            # with any free high local position (the next round then finds the rightful bit local)
+            reserved = {where[pos] for pos in wrong_pos if where[pos] < nl}
+            taken: set[int] = set()
+            gb, lp = [], []
+            for pos in wrong_pos:
+                src = where[pos]
+                if src >= nl or src in taken:
+                    src = next(p for p in range(nl - 1, -1, -1) if p not in taken and p not in reserved)
+                taken.add(src)
+                gb.append(pos - nl)
+                lp.append(src)
+            _apply_swap(ops, stats, where, n, nl, gb, lp)
         if any(where[i] != i for i in range(nl)):
             # new bit i <- old bit where[i] (logical bit i currently lives at physical where[i])
             ops.append(Op("permute", perm=[where[i] for i in range(nl)]))
@@ -116,80 +142,88 @@ def plan_sharded(lowered: Sequence, n: int, g: int, restore: bool = True):
     return ops, stats, where
 
 
-def emit_remap_ordered(ops, stats, where, n, nl, new_global):
-    """Exchange so that the rank bits become `new_global`, placing logical bit b at rank position
-    b - nl whenever b >= nl is among the incoming bits and that position is being vacated."""
+def _apply_swap(ops, stats, where, n, nl, gbits, lpos):
+    """Record the exchange that swaps rank position nl + gbits[j] with local position lpos[j] and update
+    `where` (logical bit -> physical position)."""
+    s = len(gbits)
+    if s == 0:
+        return
+    inv = [0] * n
+    for b in range(n):
+        inv[where[b]] = b
+    # the kernels take ascending rank-bit order (digit bit j <-> gbits[j])
+    pairs = sorted(zip(gbits, lpos))
+    gbits = [x for x, _ in pairs]
+    lpos = [y for _, y in pairs]
+    ops.append(Op("exchange", gbits=gbits, lpos=lpos))
+    stats["exchanges"] += 1
+    stats["exchange_bits"] += s
+    stats["moved_shard_fraction"] += (2 ** s - 1) / 2 ** s
+    for gb, lp in zip(gbits, lpos):
+        b_rank, b_loc = inv[nl + gb], inv[lp]
+        where[b_rank], where[b_loc] = lp, nl + gb
+
+
+def emit_exchange(ops, stats, where, n, nl, new_global):
+    """Exchange so that the rank bits become the logical bits `new_global`: every rank position whose
+    occupant is not in `new_global` is swapped with the local position of an incoming bit, placing logical bit
+    b at rank position b whenever b >= nl is incoming and that position is being vacated."""
     cur_global = [b for b in range(n) if where[b] >= nl]
     s_out = sorted([b for b in cur_global if b not in new_global], key=lambda b: where[b])
     s_in = [b for b in new_global if b not in cur_global]
     s = len(s_out)
     if s == 0:
         return
-    # match incoming bits to vacated rank positions
     slots = [where[b] for b in s_out]                 # physical rank positions being vacated
     assigned = [None] * s
     rest = []
     for b in s_in:
         if b >= nl and b in slots:
-            assigned[slots.index(b)] = b
+            assigned[slots.index(b)] = b              # home position
         else:
             rest.append(b)
     for j in range(s):
         if assigned[j] is None:
             assigned[j] = rest.pop(0)
-    s_in = assigned
-    inv = [0] * n
-    for b in range(n):
-        inv[where[b]] = b
-    perm = list(range(nl))
-    moved = False
-    for j, b in enumerate(s_in):
-        tgt = nl - s + j
-        src = where[b]
-        if src != tgt:
-            other = inv[tgt]
-            perm[tgt], perm[src] = perm[src], perm[tgt]
-            where[b], where[other] = tgt, src
-            inv[tgt], inv[src] = b, other
-            moved = True
-    if moved:
-        ops.append(Op("permute", perm=perm))
-        stats["permutes"] += 1
-    ops.append(Op("exchange", gbits=[p - nl for p in slots]))
-    stats["exchanges"] += 1
-    stats["exchange_bits"] += s
-    stats["moved_shard_fraction"] += (2 ** s - 1) / 2 ** s
-    for j, (bo, bi) in enumerate(zip(s_out, s_in)):
-        where[bo], where[bi] = nl - s + j, slots[j]
+    _apply_swap(ops, stats, where, n, nl, [p - nl for p in slots], [where[b] for b in assigned])
 
 
 # ------------------------------------------------------------------------------------------
-# exchange
+# exchange without peer mapping (gloo CPU tests, GPUs without P2P): send/recv of gathered pieces
 # ------------------------------------------------------------------------------------------
-def exchange(dist, src, dst, rank: int, gbits: Sequence[int]):
-    """Swap rank bits `gbits` (ascending) with the top s = len(gbits) local index bits.
-    `src`, `dst`: 1-D tensors holding the shard; the result is written to `dst`.
-    Chunk D of the shard (value of the top s local bits) goes to the rank whose bits `gbits`
-    equal D and is replaced by that rank's chunk number my_bits."""
+def exchange_sendrecv(dist, src, dst, rank: int, gbits: Sequence[int], lpos: Sequence[int]):
+    """Swap rank bits `gbits` with the local index bits `lpos` (one to one).  `src`, `dst`: 1-D tensors holding
+    the shard; the result is written to `dst`.  The amplitudes whose local bits `lpos` spell the digit D go to
+    the rank whose bits `gbits` equal D and land there at the same local index with those bits replaced by the
+    sender's own digit.  Pieces are gathered into contiguous buffers for dist.isend / irecv."""
+    import torch
     s = len(gbits)
-    chunks = 1 << s
-    size = src.numel() // chunks
     mine = 0
     for j, gb in enumerate(gbits):
         mine |= ((rank >> gb) & 1) << j
-    ops = []
-    for D in range(chunks):
+    idx = torch.arange(src.numel(), device=src.device)
+    digit = torch.zeros_like(idx)
+    for j, lp in enumerate(lpos):
+        digit |= ((idx >> lp) & 1) << j
+    sel = [torch.nonzero(digit == D).reshape(-1) for D in range(1 << s)]
+    ops, recv = [], {}
+    for D in range(1 << s):
         if D == mine:
             continue
         partner = rank
         for j, gb in enumerate(gbits):
             partner = (partner & ~(1 << gb)) | (((D >> j) & 1) << gb)
-        ops.append(dist.P2POp(dist.isend, src[D * size:(D + 1) * size], partner))
-        ops.append(dist.P2POp(dist.irecv, dst[D * size:(D + 1) * size], partner))
+        out = src[sel[D]].contiguous()
+        recv[D] = torch.empty_like(out)
+        ops.append(dist.P2POp(dist.isend, out, partner))
+        ops.append(dist.P2POp(dist.irecv, recv[D], partner))
     reqs = dist.batch_isend_irecv(ops) if ops else []
-    dst[mine * size:(mine + 1) * size].copy_(src[mine * size:(mine + 1) * size])
+    dst[sel[mine]] = src[sel[mine]]
     for r in reqs:
         r.wait()
+    # what partner(D) sent are ITS amplitudes with local digit == mine; they land where my local digit is D
+    for D, buf in recv.items():
+        dst[sel[D]] = buf
 
 
 # ------------------------------------------------------------------------------------------
@@ -207,17 +241,55 @@ class CudaEngine:
         self._plans = {}
 
     def alloc(self):
-        return self.hb.DeviceState(self.n_local, self.ctype)
+        # own cudaMalloc blocks: peers map them with cudaIpc for the fused exchange
+        return self.hb.DeviceState(self.n_local, self.ctype, ipc=True)
 
     def tensor(self, st):
         return st.tensor
 
-    def run_gates(self, st, key, gates):
+    def _plan(self, key, gates):
         plan = self._plans.get(key)
         if plan is None:
             plan = self._plans[key] = self.hb.Plan(gates, self.n_local, self.ctype, self.plan_options)
+        return plan
+
+    def run_gates(self, st, key, gates):
+        plan = self._plan(key, gates)
         plan.run(st)
         return plan.n_passes
+
+    # -- fused exchange (peer buffers mapped over NVLink) -------------------------------------------------
+    def map_peers(self, dist, buffers):
+        """Exchange cudaIpc handles of this rank's shard buffers with every rank and map the peers' buffers.
+        Returns ptrs[buffer index][rank] (own buffers: their own pointers) or None when peer mapping is not
+        possible (then the runner falls back to send/recv)."""
+        from .state import open_ipc
+        rank, world = dist.get_rank(), dist.get_world_size()
+        try:
+            mine = [b.raw.ipc_handle() for b in buffers]
+        except Exception:
+            mine = None
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if any(h is None for h in gathered):
+            return None
+        ptrs = [[0] * world for _ in buffers]
+        ok = 1
+        try:
+            for r in range(world):
+                for i, b in enumerate(buffers):
+                    ptrs[i][r] = b.ptr.value if r == rank else open_ipc(gathered[r][i], b.device)
+        except Exception:
+            ok = 0
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        return ptrs if all(flags) else None
+
+    def run_gates_xchg(self, st, key, gates, digit, lpos, dst_ptrs):
+        """Local gates (may be empty) with the exchange fused into the write-back of the last pass."""
+        plan = self._plan(key, gates)
+        plan.run_xchg(st, digit, lpos, dst_ptrs)
+        return max(1, plan.n_passes)
 
     def permute(self, st, key, perm):
         plan = self._plans.get(key)
@@ -275,6 +347,14 @@ class ShardedRunner:
         self.engine = engine if engine is not None else CudaEngine(self.n_local, ctype, plan_options)
         self.a = self.engine.alloc()
         self.b = self.engine.alloc()
+        # fused exchange: map every rank's two shard buffers; peer[i][r] = pointer to rank r's buffer i
+        self._bufs = [self.a, self.b]
+        self._cur = 0                       # which buffer holds the state (the same on every rank)
+        self.peer = None
+        if self.g > 0 and hasattr(self.engine, "map_peers"):
+            self.peer = self.engine.map_peers(dist, self._bufs)
+        self.fused = self.peer is not None
+        self._flag = None
         self.local_passes = 0
         self.exchange_ms = 0.0
         self._count_passes = True
@@ -335,8 +415,9 @@ class ShardedRunner:
         s = self.stats
         return (f"{self.world} GPUs, top {self.g} index bits = rank; {s['crossing_gates']}/{s['gates']} gates touch a "
                 f"sharded qubit; {s['exchanges']} exchanges ({s['exchange_bits']} bit swaps, "
-                f"{s['moved_shard_fraction']:.2f} shards moved per GPU), {s['permutes']} local permutation passes, "
-                f"{self.local_passes} local tile passes per step")
+                f"{s['moved_shard_fraction']:.2f} shards moved per GPU, "
+                f"{'fused into the preceding tile pass, peer stores over NVLink' if self.fused else 'send/recv'}), "
+                f"{s['permutes']} local permutation passes, {self.local_passes} tile passes per step")
 
     def init_state(self, seed: int):
         self.engine.init_random(self.a, seed, self.rank * (2 ** self.n_local))
@@ -374,22 +455,63 @@ class ShardedRunner:
     def norm2(self) -> float:
         return self._allreduce_sum(self.engine.norm2(self.a))
 
+    def _digit_and_dst(self, op):
+        """This rank's digit over the swapped rank bits and, for every digit D, the destination buffer: the
+        not-current buffer of the rank whose bits op.gbits spell D."""
+        mine = 0
+        for j, gb in enumerate(op.gbits):
+            mine |= ((self.rank >> gb) & 1) << j
+        dst = []
+        for D in range(1 << len(op.gbits)):
+            partner = self.rank
+            for j, gb in enumerate(op.gbits):
+                partner = (partner & ~(1 << gb)) | (((D >> j) & 1) << gb)
+            dst.append(self.peer[1 - self._cur][partner])
+        return mine, dst
+
+    def _barrier_and_swap(self):
+        """After a fused exchange: every rank must have finished writing into everybody's buffers before anyone
+        reads its own -- one 1-element all-reduce in stream order -- then the two buffers swap roles."""
+        import torch
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=self.engine.tensor(self.a).device)
+        self.dist.all_reduce(self._flag)
+        self.a, self.b = self.b, self.a
+        self._cur ^= 1
+
     def step(self, time_exchange: bool = False):
         passes = 0
-        for i, op in enumerate(self.ops):
+        ops = self.ops
+        i = 0
+        while i < len(ops):
+            op = ops[i]
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            if self.fused and op.kind == "local" and nxt is not None and nxt.kind == "exchange":
+                mine, dst = self._digit_and_dst(nxt)
+                passes += self.engine.run_gates_xchg(self.a, ("g", self._segment, i), op.gates, mine, nxt.lpos, dst)
+                self._barrier_and_swap()
+                i += 2
+                continue
             if op.kind == "local":
                 passes += self.engine.run_gates(self.a, ("g", self._segment, i), op.gates)
             elif op.kind == "permute":
                 passes += self.engine.permute(self.a, ("p", self._segment, i), op.perm)
+            elif self.fused:
+                mine, dst = self._digit_and_dst(op)
+                passes += self.engine.run_gates_xchg(self.a, ("x", self._segment, i), [], mine, op.lpos, dst)
+                self._barrier_and_swap()
             else:
                 if time_exchange:
                     self.engine.sync()
                     t0 = time.perf_counter()
-                exchange(self.dist, self.engine.tensor(self.a), self.engine.tensor(self.b), self.rank, op.gbits)
+                exchange_sendrecv(self.dist, self.engine.tensor(self.a), self.engine.tensor(self.b), self.rank,
+                                  op.gbits, op.lpos)
                 self.a, self.b = self.b, self.a
+                self._cur ^= 1
                 if time_exchange:
                     self.engine.sync()
                     self.exchange_ms += 1e3 * (time.perf_counter() - t0)
+            i += 1
         self.local_passes = passes
 
     def kernel_time_ms(self, reps: int = 2) -> float:

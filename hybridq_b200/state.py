@@ -113,6 +113,20 @@ class Plan:
                                             _stream_handle(stream, state.device)), "hq_plan_run_range")
 
 
+    def run_xchg(self, state: "DeviceState", gbit_digit: int, lpos: Sequence[int], dst_ptrs: Sequence[int], stream=None):
+        """All passes, the last one with its write-back redirected (hq_plan_run_range_xchg): the amplitudes whose
+        local index bits `lpos` spell D go to the buffer `dst_ptrs[D]` at the same index with those bits replaced
+        by `gbit_digit`.  A plan without passes becomes one gate-less redirect pass."""
+        if state.n_qubits != self.n_qubits or state.dtype != self.dtype:
+            raise ValueError("plan and state disagree on size or precision")
+        s = len(lpos)
+        pos = (ctypes.c_uint32 * 4)(*(list(lpos) + [0] * (4 - s)))
+        dst = (ctypes.c_void_p * 8)(*([int(p) for p in dst_ptrs] + [None] * (8 - len(dst_ptrs))))
+        with _on(state.device):
+            check(lib.hq_plan_run_range_xchg(self._h, state.ptr, 0, self.n_passes, s, int(gbit_digit), pos, dst,
+                                             _stream_handle(stream, state.device)), "hq_plan_run_range_xchg")
+
+
 class BitPermPlan:
     """In-place permutation of index bits as tile passes (hq_plan_create_bitperm):
     new index bit i <- old index bit perm[i]."""
@@ -144,8 +158,55 @@ class BitPermPlan:
             check(lib.hq_plan_run(self._h, state.ptr, _stream_handle(stream, state.device)), "hq_plan_run")
 
 
+class RawDeviceBuffer:
+    """A cudaMalloc'ed block owned by this object (hq_malloc / hq_free), exposed to torch through
+    ``__cuda_array_interface__``.  Shard buffers that peers map over NVLink are allocated this way: a
+    cudaIpc handle needs the BASE pointer of an allocation, which a block carved out of torch's caching
+    allocator is not."""
+
+    def __init__(self, nbytes: int, device: int):
+        self.device = int(device)
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        with _on(self.device):
+            check(lib.hq_malloc(ctypes.byref(p), self.nbytes), "hq_malloc")
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self, complex_type):
+        import torch
+        t = torch.as_tensor(self, device=f"cuda:{self.device}")
+        return t.view(_torch_ctype(complex_type))
+
+    def ipc_handle(self) -> bytes:
+        h = ctypes.create_string_buffer(64)
+        with _on(self.device):
+            check(lib.hq_ipc_get_handle(ctypes.c_void_p(self.ptr), h), "hq_ipc_get_handle")
+        return h.raw
+
+    def __del__(self):
+        p, self.ptr = getattr(self, "ptr", None), None
+        if p:
+            try:
+                with _on(self.device):
+                    lib.hq_free(ctypes.c_void_p(p))
+            except Exception:
+                pass
+
+
+def open_ipc(handle: bytes, device: int) -> int:
+    """Map a peer's RawDeviceBuffer into this process for kernels running on `device` (cudaIpcOpenMemHandle with
+    lazy peer access); returns the device pointer."""
+    p = ctypes.c_void_p()
+    with _on(device):
+        check(lib.hq_ipc_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(p)), "hq_ipc_open")
+    return p.value
+
+
 class DeviceState:
-    def __init__(self, n_qubits: int, complex_type="complex64", device: int | None = None, tensor=None):
+    def __init__(self, n_qubits: int, complex_type="complex64", device: int | None = None, tensor=None,
+                 ipc: bool = False):
         import torch
         if not torch.cuda.is_available():
             raise _lib.HybridQB200Error("hybridq_b200 needs a CUDA device (no CPU fallback)")
@@ -155,6 +216,11 @@ class DeviceState:
         if device is None:
             device = torch.cuda.current_device()
         self.device = int(device)
+        self.raw = None
+        if tensor is None and ipc:
+            # own cudaMalloc block, so that peers can map it (see RawDeviceBuffer)
+            self.raw = RawDeviceBuffer((2 ** self.n_qubits) * self.complex_type.itemsize, self.device)
+            tensor = self.raw.tensor(self.complex_type)
         if tensor is None:
             with torch.cuda.device(self.device):
                 tensor = torch.empty(2 ** self.n_qubits, dtype=_torch_ctype(complex_type),

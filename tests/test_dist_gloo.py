@@ -1,6 +1,8 @@
 """N > 1 path on CPU: world_size 2 and 4 over gloo.  Checks hybridq_b200.dist's schedule
-(Belady remapping of rank bits, local permutation, pairwise / grouped chunk exchange,
-restoration of the canonical order) against a single-process oracle evolution."""
+(Belady remapping of rank bits, in-place rank-bit <-> local-bit swaps, restoration of the
+canonical order) and the send/recv form of the exchange against a single-process oracle evolution.
+(The fused NVLink form of the exchange is GPU-only: tests/test_gpu_ring.py plays it on one GPU,
+tests/dist_gpu_worker.py on two.)"""
 import os
 import subprocess
 import sys
@@ -64,7 +66,7 @@ def test_schedule_model_single_process(oracle):
     from hybridq_b200.dist import plan_sharded
     from hybridq_b200.circuits import sharded_circuit, to_positions
     rng = np.random.default_rng(0)
-    for n, g in ((10, 1), (11, 2), (12, 3)):
+    for n, g in ((10, 1), (11, 2), (12, 3), (14, 2), (15, 3)):
         nl = n - g
         lowered, _ = to_positions(sharded_circuit(n, g, depth=6, frac_global=0.3, seed=n), qubits=list(range(n)))
         psi = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
@@ -80,10 +82,10 @@ def test_schedule_model_single_process(oracle):
             elif op.kind == "permute":
                 st = oracle.numpy_swap(st, list(op.perm) + list(range(nl, n)))
             else:
-                s = len(op.gbits)
-                perm = list(range(n))
-                for j, gb in enumerate(op.gbits):
-                    perm[nl - s + j], perm[nl + gb] = nl + gb, nl - s + j
+                perm = list(range(n))                      # rank bit gb <-> local bit lp, in place
+                for gb, lp in zip(op.gbits, op.lpos):
+                    assert lp < nl
+                    perm[lp], perm[nl + gb] = nl + gb, lp
                 st = oracle.numpy_swap(st, perm)
         assert sorted(done) == list(range(len(lowered)))
         assert where == list(range(n))

@@ -90,17 +90,17 @@ def test_lane_mapping_is_bank_conflict_free():
 
 def test_merging_follows_the_measured_cost_table():
     """In-pass merging (hq_plan.cpp measured_cost).  complex128 (tensor-core path from k = 2): two k = 2 gates
-    sharing a bit become one k = 3 matrix.  complex64 (FFMA2 slots up to k = 3, measured 0.62 / 1.36 ms): the same
-    (1.36 vs 1.24 is within the 10 % slack the greedy merge grants, because the k = 3 cluster then absorbs every
-    later gate on its bits: a triangle of three k = 2 gates becomes one matrix).  Always: disjoint k = 2 gates stay
-    apart, a 1-qubit gate is absorbed by a neighbour."""
+    sharing a bit become one k = 3 matrix.  complex64 (FFMA2 slots up to k = 3, measured 0.62 / 1.36 ms): a chain of
+    two k = 2 gates stays two matrices (1.24 < 1.36), a triangle of three becomes one k = 3 (the greedy pairwise
+    merge is granted 10 % slack so that it can get there, and a second look splits the clusters that did not pay).
+    Always: disjoint k = 2 gates stay apart, a 1-qubit gate is absorbed by a neighbour."""
     from helpers import Emu
     emu = Emu()
     n = 14
     for dtype in (0, 1):
         def mats(gates, opts=None):
             return sum(p["n_kernel_gates"] for p in emu.plan(dtype, n, gates, opts))
-        assert mats([[3, 5], [5, 8]]) == 1                      # chain -> k = 3
+        assert mats([[3, 5], [5, 8]]) == (2 if dtype == 0 else 1)      # chain -> k = 3 only where that is cheaper
         assert mats([[3, 5], [7, 8]]) == 2                      # disjoint -> two matrices
         assert mats([[3, 5], [5]]) == 1 and mats([[4], [4, 9]]) == 1
         assert mats([[3, 5], [5, 8], [8, 3]]) == 1              # triangle on 3 bits -> one k = 3
