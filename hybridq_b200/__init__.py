@@ -13,7 +13,7 @@ missing: there is no CPU fallback.  Public surface:
 """
 from ._lib import lib, PlanOptions, HybridQB200Error, DROPIN_DIR, LIBPATH  # noqa: F401
 from .state import DeviceState, Plan, BitPermPlan  # noqa: F401
-from .simulate import simulate, expectation_value  # noqa: F401
+from .simulate import simulate, expectation_value, clear_caches, sharded_runner  # noqa: F401
 from .dot import dot, transpose, to_complex  # noqa: F401
 from . import circuits  # noqa: F401
 

@@ -109,6 +109,7 @@ _proto("hq_plan_num_passes", ctypes.c_int, _vp)
 _proto("hq_plan_num_gates", ctypes.c_int, _vp)
 _proto("hq_plan_num_kernel_gates", ctypes.c_int, _vp)
 _proto("hq_plan_flops", ctypes.c_double, _vp)
+_proto("hq_plan_arith_counts", ctypes.c_int, _vp, _u32p, ctypes.c_int)
 _proto("hq_plan_pass_info", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int)
 _proto("hq_plan_pass_gates", ctypes.c_int, _vp, ctypes.c_int, _u32p, ctypes.c_int)
 _proto("hq_plan_run", ctypes.c_int, _vp, _vp, _vp)
@@ -131,7 +132,7 @@ EXPORTED = [
     "hq_stream_sync", "hq_apply_U_dev", "hq_apply_U_direct_dev", "hq_swap_dev", "hq_pack_dev",
     "hq_unpack_dev", "hq_init_product_dev", "hq_init_random_dev", "hq_norm2_dev", "hq_vdot_dev",
     "hq_scale_dev", "hq_marginal_dev", "hq_project_dev", "hq_marginal_cond_dev", "hq_project_mask_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
-    "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_flops", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
+    "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_flops", "hq_plan_arith_counts", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
     "hq_plan_run_range_xchg", "hq_ipc_get_handle", "hq_ipc_open", "hq_ipc_close", "hq_set_ring",
     "hq_set_tuning", "hq_launch_count", "hq_launch_count_reset",
 ]

@@ -332,7 +332,8 @@ class CudaEngine:
 class ShardedRunner:
     """Executes a sharded schedule; one instance per rank."""
 
-    def __init__(self, n: int, lowered: Sequence, ctype, dist, engine=None, plan_options=None, restore=True):
+    def __init__(self, n: int, lowered: Sequence, ctype, dist, engine=None, plan_options=None, restore=True,
+                 key=None):
         self.dist = dist
         self.rank = dist.get_rank()
         self.world = dist.get_world_size()
@@ -342,7 +343,11 @@ class ShardedRunner:
         self.n = n
         self.n_local = n - self.g
         self.ctype = np.dtype(ctype)
+        self._schedules = {}                # circuit key -> (ops, stats, final_where)
+        self._segment = key if key is not None else 0
         self.ops, self.stats, self.final_where = plan_sharded(lowered, n, self.g, restore=restore)
+        if key is not None:
+            self._schedules[key] = (self.ops, dict(self.stats), self.final_where)
         self.n_gates = len(lowered)
         self.engine = engine if engine is not None else CudaEngine(self.n_local, ctype, plan_options)
         self.a = self.engine.alloc()
@@ -358,17 +363,44 @@ class ShardedRunner:
         self.local_passes = 0
         self.exchange_ms = 0.0
         self._count_passes = True
-        self._segment = 0
         self.complex_type = self.ctype
 
-    def replan(self, lowered: Sequence, restore: bool = True):
+    def replan(self, lowered: Sequence, restore: bool = True, key=None, accumulate: bool = True):
         """Swap in the schedule of another gate list (the next segment of a circuit that is interrupted by
-        measurement gates); the shard buffers and their contents stay."""
-        self.ops, stats, self.final_where = plan_sharded(lowered, self.n, self.g, restore=restore)
-        for k, v in stats.items():
-            self.stats[k] = self.stats.get(k, 0) + v
-        self.n_gates += len(lowered)
-        self._segment += 1
+        measurement gates, or another circuit on a reused runner); the shard buffers and their contents stay.
+        `key` (hashable) identifies the gate list: schedules and the engine's compiled plans are cached under
+        it, so running the same circuit again costs no planning."""
+        if key is not None and key in self._schedules:
+            self.ops, stats, self.final_where = self._schedules[key]
+        else:
+            self.ops, stats, self.final_where = plan_sharded(lowered, self.n, self.g, restore=restore)
+            if key is not None:
+                self._schedules[key] = (self.ops, dict(stats), self.final_where)
+        if accumulate:
+            for k, v in stats.items():
+                self.stats[k] = self.stats.get(k, 0) + v
+            self.n_gates += len(lowered)
+        else:
+            self.stats = dict(stats)
+            self.n_gates = len(lowered)
+        self._segment = key if key is not None else (self._segment + 1 if isinstance(self._segment, int) else 1)
+
+    def close(self):
+        """Unmap the peers' buffers and release this rank's (collective: every rank must call it)."""
+        from ._lib import lib
+        import ctypes
+        if self.peer is not None:
+            for table in self.peer:
+                for r, p in enumerate(table):
+                    if r != self.rank and p:
+                        lib.hq_ipc_close(ctypes.c_void_p(p))
+            self.peer = None
+            self.fused = False
+        self.engine.sync()
+        self.dist.barrier()
+        self.a = self.b = None
+        self._bufs = []
+        self.engine._plans.clear() if hasattr(self.engine, "_plans") else None
 
     # -- measurement support on the sharded state (canonical bit order required: call between segments) ------
     def marginal(self, pos: Sequence[int]):

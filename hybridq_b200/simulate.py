@@ -26,8 +26,64 @@ from warnings import warn
 
 import numpy as np
 
+import hashlib
+from collections import OrderedDict
+
 from ._lib import PlanOptions
 from .state import DeviceState, Plan
+
+# Compiled plans are cached by the content of the gate stream: calling simulate() again with the same circuit (a
+# parameter scan over initial states, a benchmark loop) costs no planning and no program upload.
+_PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
+_PLAN_CACHE_MAX = 16
+_RUNNERS: dict = {}          # (n_qubits, complex type, world size, plan options) -> ShardedRunner
+
+
+def _gates_key(gates, n_qubits, complex_type, opts) -> tuple:
+    h = hashlib.blake2b(digest_size=16)
+    for U, pos in gates:
+        h.update(np.ascontiguousarray(U, dtype=np.complex128).tobytes())
+        h.update(np.asarray(pos, dtype=np.int64).tobytes())
+        h.update(b"|")
+    o = tuple(getattr(opts, f) for f, _ in opts._fields_) if opts is not None else None
+    return (h.hexdigest(), len(gates), int(n_qubits), str(np.dtype(complex_type)), o)
+
+
+def _cached_plan(gates, n_qubits, complex_type, opts) -> Plan:
+    key = _gates_key(gates, n_qubits, complex_type, opts)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = Plan(gates, n_qubits, complex_type, opts)
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+            _PLAN_CACHE.popitem(last=False)
+    else:
+        _PLAN_CACHE.move_to_end(key)
+    return plan
+
+
+def clear_caches() -> None:
+    """Drop the cached plans and release the cached sharded runners (their shard buffers and peer mappings).
+    Collective when a sharded runner exists: every rank must call it."""
+    _PLAN_CACHE.clear()
+    for r in list(_RUNNERS.values()):
+        r.close()
+    _RUNNERS.clear()
+
+
+def sharded_runner(n_qubits, complex_type, dist, plan_options=None):
+    """The (cached) :class:`hybridq_b200.dist.ShardedRunner` simulate(shard=True) uses for this state size: two
+    shard buffers per GPU, mapped by every peer over NVLink.  Collective."""
+    from .dist import ShardedRunner
+    o = tuple(getattr(plan_options, f) for f, _ in plan_options._fields_) if plan_options is not None else None
+    key = (int(n_qubits), str(np.dtype(complex_type)), dist.get_world_size(), o)
+    r = _RUNNERS.get(key)
+    if r is None:
+        for old in list(_RUNNERS.values()):       # one resident sharded state at a time
+            old.close()
+        _RUNNERS.clear()
+        r = _RUNNERS[key] = ShardedRunner(n_qubits, [], complex_type, dist, plan_options=plan_options)
+    return r
 
 
 def _try_hybridq():
@@ -174,6 +230,9 @@ def simulate(circuit,
             gates = [g for g in gates if getattr(g, "name", None) != "I"]
     n_qubits = len(qubits)
 
+    dist = _dist_if_sharded(kwargs["shard"])
+    n_shard_bits = int(round(np.log2(dist.get_world_size()))) if dist is not None else 0
+
     # initial / final state checks (simulation.py:261-286, :415-426)
     def _prepare(state):
         if isinstance(state, str):
@@ -187,7 +246,7 @@ def simulate(circuit,
         state = np.asarray(state)
         if any(x != 2 for x in state.shape):
             raise ValueError("Only qubits of dimension 2 are supported.")
-        if state.ndim != n_qubits:
+        if state.ndim != n_qubits and not (n_shard_bits and state.ndim == n_qubits - n_shard_bits):
             raise ValueError("Wrong number of qubits for initial/final state.")
         return state
 
@@ -230,7 +289,6 @@ def simulate(circuit,
         segments.append(("gates", cur))
     t_pre = time.perf_counter() - t_pre
 
-    dist = _dist_if_sharded(kwargs["shard"])
     if dist is not None and kwargs["shard"] == "auto":
         g_bits = int(round(np.log2(dist.get_world_size())))
         kmax = max((len(p) for kind, seg in segments if kind == "gates" for _, p in seg), default=0)
@@ -242,7 +300,7 @@ def simulate(circuit,
 
     t_plan = time.perf_counter()
     opts: PlanOptions | None = kwargs["plan_options"]
-    plans = [(kind, Plan(payload, n_qubits, complex_type, opts) if kind == "gates" else payload)
+    plans = [(kind, _cached_plan(payload, n_qubits, complex_type, opts) if kind == "gates" else payload)
              for kind, payload in segments]
     t_plan = time.perf_counter() - t_plan
 
@@ -322,19 +380,22 @@ def _dist_if_sharded(shard):
 
 
 def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwargs, t_pre):
-    """Multi-GPU evolution (hybridq_b200.dist): every rank calls simulate() with the same circuit; an
-    array initial state is the FULL state on every rank (each uploads its own slice).  Returns this rank's shard
-    of the final state
-    (amplitudes [rank * 2^(n-g), (rank+1) * 2^(n-g)) in canonical order).  The reference has no
-    counterpart (simulation.py:379-380)."""
-    from .dist import ShardedRunner
+    """Multi-GPU evolution (hybridq_b200.dist): every rank calls simulate() with the same circuit.  An array
+    initial state is either the FULL state on every rank (each uploads its own slice) or, with ndim =
+    n - log2(world), this rank's shard (amplitudes [rank * 2^(n-g), (rank+1) * 2^(n-g)) of the full state).
+    Returns this rank's shard of the final state in canonical order.  The runner (shard buffers, peer mappings)
+    and the schedules / compiled plans are cached across calls.  The reference has no counterpart
+    (simulation.py:379-380)."""
     for kind, payload in segments:
         if kind != "gates" and getattr(payload, "name", None) not in ("PROJECTION", "MEASURE"):
             raise NotImplementedError("only Projection and Measure FunctionalGates are supported on a sharded state")
     qmap = kwargs.pop("_qmap")
     t_plan = time.perf_counter()
-    first = segments[0][1] if segments and segments[0][0] == "gates" else []
-    runner = ShardedRunner(n_qubits, first, complex_type, dist, plan_options=kwargs["plan_options"])
+    runner = sharded_runner(n_qubits, complex_type, dist, kwargs["plan_options"])
+    runner.stats = {}
+    runner.n_gates = 0
+    keys = [(_gates_key(payload, n_qubits, complex_type, None)[0] if kind == "gates" else None)
+            for kind, payload in segments]
     t_plan = time.perf_counter() - t_plan
     nl = runner.n_local
     t_up = time.perf_counter()
@@ -342,23 +403,21 @@ def _simulate_sharded(dist, segments, n_qubits, complex_type, initial_state, kwa
         runner.init_product(initial_state)
     else:
         flat = np.asarray(initial_state).reshape(-1)
-        flat = flat[runner.rank * 2 ** nl:(runner.rank + 1) * 2 ** nl]
-        runner.load_shard(np.ascontiguousarray(flat, dtype=complex_type))
-    runner.engine.sync()
+        if flat.size == 2 ** n_qubits:
+            flat = flat[runner.rank * 2 ** nl:(runner.rank + 1) * 2 ** nl]
+        runner.load_shard(flat if flat.dtype == complex_type and flat.flags.c_contiguous
+                          else np.ascontiguousarray(flat, dtype=complex_type))
     t_up = time.perf_counter() - t_up
-    dist.barrier()
     t0 = time.perf_counter()
-    for si, (kind, payload) in enumerate(segments):
+    for (kind, payload), key in zip(segments, keys):
         if kind == "gates":
-            if si > 0:
-                runner.replan(payload)
+            runner.replan(payload, key=key)
             runner.step()
         elif payload.name == "PROJECTION":
             _apply_projection(payload, runner, qmap)
         else:
             _apply_measure(payload, runner, qmap)
     runner.engine.sync()
-    dist.barrier()
     runtime = time.perf_counter() - t0
     info = {"runtime (s)": runtime, "pre-pass (s)": t_pre, "plan (s)": t_plan, "upload (s)": t_up,
             "n_gate_applies": runner.n_gates, "n_passes": runner.local_passes, "n_qubits": n_qubits,

@@ -91,6 +91,19 @@ class Plan:
             lib.hq_plan_destroy(h)
             self._h = None
 
+    def arithmetic(self) -> dict:
+        """{'k2': {'ffma2_slots': .., 'tensor_cores': .., 'fma_generic': .., 'two_phase': ..}, ...}: how many
+        kernel matrices of each size run on which arithmetic (hq_plan_arith_counts)."""
+        out = (ctypes.c_uint32 * 32)()
+        check(lib.hq_plan_arith_counts(self._h, out, 32), "hq_plan_arith_counts")
+        names = ("ffma2_slots", "tensor_cores", "fma_generic", "two_phase")
+        res = {}
+        for k in range(1, 9):
+            row = {names[a]: int(out[4 * (k - 1) + a]) for a in range(4) if out[4 * (k - 1) + a]}
+            if row:
+                res[f"k{k}"] = row
+        return res
+
     def pass_info(self, p: int) -> dict:
         out = (ctypes.c_uint32 * 32)()
         check(lib.hq_plan_pass_info(self._h, p, out, 32), "hq_plan_pass_info")
