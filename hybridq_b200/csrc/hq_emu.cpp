@@ -15,7 +15,7 @@
 namespace {
 
 void emu_fast_slot(float4* tile, int s, const HqGateDesc* g, const HqPassHeader& ph, int Tu, int tid) {
-  hq::gate_fast_f32<-1, 3>(tile, g, ph, uint32_t(s), Tu, tid);
+  hq::gate_fast_f32<-1, 3>(tile, hq::load_stream_regs(g, tid), ph, uint32_t(s), Tu, tid);
 }
 void emu_fast_slot(double2*, int, const HqGateDesc*, const HqPassHeader&, int, int) {}
 

@@ -224,7 +224,7 @@ struct GroupSync {
 // (inlined on purpose: `ph` must stay the kernel's own __grid_constant__ parameter for its elements to be
 // constant-bank operands; behind a call it decays to a generic pointer and every element becomes an LD)
 template <int MAXK>
-__device__ __forceinline__ void gate_fast_slot(float4* tile, const HqGateDesc* g, const HqPassHeader& ph, uint32_t slot,
+__device__ __forceinline__ void gate_fast_slot(float4* tile, const StreamRegs& g, const HqPassHeader& ph, uint32_t slot,
                                                int Tu, int tid) {
 #if HQ_FAST_TEMPLATED
   switch (slot) {
@@ -242,7 +242,7 @@ __device__ __forceinline__ void gate_fast_slot(float4* tile, const HqGateDesc* g
 #endif
 }
 template <int MAXK>
-__device__ __forceinline__ void gate_fast_slot(double2*, const HqGateDesc*, const HqPassHeader&, uint32_t, int, int) {}
+__device__ __forceinline__ void gate_fast_slot(double2*, const StreamRegs&, const HqPassHeader&, uint32_t, int, int) {}
 
 // Every gate of the pass on one tile held in shared memory; `sync` separates consecutive gates and is also
 // called after the last one (the drain reads what other threads wrote).
@@ -257,13 +257,19 @@ __device__ __forceinline__ void apply_pass_gates(typename Traits<T>::Unit* tile,
   const int MAXK = KCLASS == 0 ? 2 : (KCLASS == 1 ? 3 : 4);
   const int MMAK = KCLASS == 3 ? HQ_MMA_MAX_K : MAXK;
   const uint32_t n_gates = ph.n_gates;
+  const bool any_fast = FAST && V == 1 && KCLASS <= 1 && ph.fast_mask != 0;
+  StreamRegs sr;
+  if (any_fast && (ph.fast_mask & 1u)) sr = load_stream_regs(gates, tid);
   for (uint32_t gi = 0; gi < n_gates; ++gi) {
     const HqGateDesc* g = gates + gi;
-    if (FAST && V == 1 && KCLASS <= 1 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
-      gate_fast_slot<MAXK>(tile, g, ph, gi, Tu, tid);       // complex64 k <= 3: constant-bank FFMA2
+    if (any_fast && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
+      gate_fast_slot<MAXK>(tile, sr, ph, gi, Tu, tid);       // complex64 k <= 3: constant-bank FFMA2
+      // the next slot gate's addressing constants travel while this thread waits at the barrier
+      if (gi + 1 < n_gates && gi + 1 < HQ_FAST_SLOTS && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
       sync();
       continue;
     }
+    if (any_fast && gi + 1 < n_gates && gi + 1 < HQ_FAST_SLOTS && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
     const uint32_t k = __ldg(&g->k);
     const uint32_t mat_off = __ldg(&g->mat_off);
     const uint32_t kind = __ldg(&g->kind);

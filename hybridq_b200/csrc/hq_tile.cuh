@@ -259,8 +259,24 @@ HQ_DEV void ffma2_bcast(F2& acc, const F2& x, float s) {
 //        true : matrix bit 0 is amplitude bit 0: K = KK + 1, a unit holds columns 2j, 2j + 1 of ONE group.
 //   S    slot index when it is known at compile time (every matrix element is then a constant-bank operand at
 //        an immediate offset), -1 = use the run-time `slot`
+// The per-thread addressing constants of a slot gate (13 table entries).  The kernel loads them for gate g + 1
+// right before the barrier that ends gate g, so their L1 latency is spent waiting at the barrier.
+struct StreamRegs {
+  uint32_t st;
+  IterBasis ib;
+  uint32_t xo[8];
+};
+HQ_DEV StreamRegs load_stream_regs(const HqGateDesc* __restrict__ g, int tid) {
+  StreamRegs r;
+  r.st = HQ_LDG(&g->tbl_thread[tid]);
+  r.ib = load_iter_basis(g->tbl_iter);
+  HQ_UNROLL
+  for (int m = 0; m < 8; ++m) r.xo[m] = HQ_LDG(&g->tbl_x[m]);
+  return r;
+}
+
 template <int KK, bool LOW, int S>
-HQ_DEV void gate_stream_f32(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph, uint32_t slot,
+HQ_DEV void gate_stream_f32(float4* tile, const StreamRegs& sr, const HqPassHeader& ph, uint32_t slot,
                             int Tu, int tid) {
   const int UD = 1 << KK;                    // units per work item
   const int DIM = LOW ? 2 * UD : UD;         // matrix dimension
@@ -268,24 +284,47 @@ HQ_DEV void gate_stream_f32(float4* tile, const HqGateDesc* __restrict__ g, cons
   const uint32_t nwork = 1u << nq;
   if (uint32_t(tid) >= nwork) return;
   const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
-  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
-  const IterBasis ib = load_iter_basis(g->tbl_iter);
+  const uint32_t st = sr.st;
+  const IterBasis ib = sr.ib;
   uint32_t xo[UD];
   HQ_UNROLL
-  for (int m = 0; m < UD; ++m) xo[m] = HQ_LDG(&g->tbl_x[m]);
+  for (int m = 0; m < UD; ++m) xo[m] = sr.xo[m];
   // matrix element e of the slot: straight out of the constant bank (row-major, (re, im) interleaved)
 #define HQ_FAST_U(e) (S >= 0 ? ph.fast_u[S >= 0 ? S : 0][e] : ph.fast_u[slot][e])
+  // software pipeline over the work items of this thread: the shared loads of item it + 1 are issued before the
+  // FFMA2 block of item it, so their latency hides behind 16 * 4^KK independent FFMA2 (different items never
+  // share a slot, so loading ahead of the previous item's stores is safe)
+  // MEASURED (profiles/r02/sweep_ring_c.jsonl): this costs the k = 2 gates 8 % (4.36 vs 4.02 ms for a 4-gate pass at
+  // n = 30: the extra 16 live registers and moves outweigh the hidden latency when 24 warps per SM already
+  // interleave), so it is compiled out by default.
+#ifndef HQ_STREAM_PREFETCH
+#define HQ_STREAM_PREFETCH 0
+#endif
+  const bool PREFETCH = HQ_STREAM_PREFETCH && UD <= 4;
+  float4 v[UD];
+  if (PREFETCH) {
+    const uint32_t sb0 = st ^ iter_offset(ib, 0);
+    HQ_UNROLL
+    for (int m = 0; m < UD; ++m) v[m] = tile[sb0 ^ xo[m]];
+  }
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
     const uint32_t sb = st ^ iter_offset(ib, it);
+    float4 nv[PREFETCH ? UD : 1];
+    if (PREFETCH) {
+      // (the last item re-reads itself instead of branching: the loads are simply not used)
+      const uint32_t sbn = st ^ iter_offset(ib, it + 1 < niter ? it + 1 : it);
+      HQ_UNROLL
+      for (int m = 0; m < UD; ++m) nv[m] = tile[sbn ^ xo[m]];
+    }
     if (!LOW) {
       F2 ae[DIM], ao[DIM];
       HQ_UNROLL
       for (int i = 0; i < DIM; ++i) { ae[i].lo = ae[i].hi = 0.f; ao[i].lo = ao[i].hi = 0.f; }
       HQ_UNROLL
       for (int j = 0; j < DIM; ++j) {
-        const float4 v = tile[sb ^ xo[j]];
-        const F2 e = {v.x, v.y}, ie = {-v.y, v.x}, o = {v.z, v.w}, io = {-v.w, v.z};
+        const float4 w = PREFETCH ? v[j] : tile[sb ^ xo[j]];      // (no prefetch: loaded column by column)
+        const F2 e = {w.x, w.y}, ie = {-w.y, w.x}, o = {w.z, w.w}, io = {-w.w, w.z};
         HQ_UNROLL
         for (int i = 0; i < DIM; ++i) {
           const float ur = HQ_FAST_U(2 * (i * DIM + j)), ui = HQ_FAST_U(2 * (i * DIM + j) + 1);
@@ -303,8 +342,8 @@ HQ_DEV void gate_stream_f32(float4* tile, const HqGateDesc* __restrict__ g, cons
       for (int i = 0; i < DIM; ++i) a[i].lo = a[i].hi = 0.f;
       HQ_UNROLL
       for (int ju = 0; ju < UD; ++ju) {
-        const float4 v = tile[sb ^ xo[ju]];
-        const F2 e = {v.x, v.y}, ie = {-v.y, v.x}, o = {v.z, v.w}, io = {-v.w, v.z};
+        const float4 w = PREFETCH ? v[ju] : tile[sb ^ xo[ju]];
+        const F2 e = {w.x, w.y}, ie = {-w.y, w.x}, o = {w.z, w.w}, io = {-w.w, w.z};
         HQ_UNROLL
         for (int i = 0; i < DIM; ++i) {
           const float ur0 = HQ_FAST_U(2 * (i * DIM + 2 * ju)), ui0 = HQ_FAST_U(2 * (i * DIM + 2 * ju) + 1);
@@ -319,6 +358,10 @@ HQ_DEV void gate_stream_f32(float4* tile, const HqGateDesc* __restrict__ g, cons
       for (int iu = 0; iu < UD; ++iu)
         tile[sb ^ xo[iu]] = make_float4(a[2 * iu].lo, a[2 * iu].hi, a[2 * iu + 1].lo, a[2 * iu + 1].hi);
     }
+    if (PREFETCH) {
+      HQ_UNROLL
+      for (int m = 0; m < UD; ++m) v[m] = nv[m];
+    }
   }
 }
 
@@ -326,7 +369,7 @@ HQ_DEV void gate_stream_f32(float4* tile, const HqGateDesc* __restrict__ g, cons
 
 // one fast slot: k = ph.fast_k[slot] in 1..3, low = matrix bit 0 on amplitude bit 0
 template <int S, int MAXK>
-HQ_DEV void gate_fast_f32(float4* tile, const HqGateDesc* __restrict__ g, const HqPassHeader& ph, uint32_t slot,
+HQ_DEV void gate_fast_f32(float4* tile, const StreamRegs& g, const HqPassHeader& ph, uint32_t slot,
                           int Tu, int tid) {
   const uint32_t k = ph.fast_k[slot] & 3u;
   const bool low = (ph.fast_k[slot] & 4u) != 0;
