@@ -336,6 +336,7 @@ def main():
     ap.add_argument("--no-ref-simulate", action="store_true")
     ap.add_argument("--qubits", type=int, default=0, help="override the base number of qubits (diagnostics only)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--tune", default="", help="diagnostics: hq_set_tuning(nbuf,ctas_per_sm,use_direct), e.g. 2,0,-1")
     ap.add_argument("--plan-options", default="", help="diagnostics: comma-separated PlanOptions fields "
                     "(tile_bits,min_run_bits,fuse,max_gates_per_pass,lookahead,merge_max_k,merge_pass_cost,fast_slots,mma_min_k)")
     args = ap.parse_args()
@@ -364,6 +365,8 @@ def main():
     n, gates, lowered, name = workload(world)
     steps, warmup = args.steps, max(args.warmup, 3)
     hb.lib.hq_launch_count_reset()
+    if args.tune:
+        hb.lib.hq_set_tuning(*[int(x) for x in args.tune.split(",")])
 
     plan_opts = hb.PlanOptions(*[int(x) for x in args.plan_options.split(",")]) if args.plan_options else None
     if world == 1:

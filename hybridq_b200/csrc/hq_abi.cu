@@ -531,12 +531,13 @@ double hq_plan_flops(const hq_plan* plan) {
   return f;
 }
 
-/* out[4 * (k - 1) + a] = number of kernel matrices of k = 1..8 qubits that run on arithmetic a:
+/* out[5 * (k - 1) + a] = number of kernel matrices of k = 1..8 qubits that run on arithmetic a:
  * 0 = constant-bank FFMA2 slot (complex64), 1 = tensor cores (mma.sync), 2 = generic FMA register / row-pair path,
- * 3 = two-phase path (k >= 5 without tensor cores); lone k <= 3 gates that take the direct kernel count as 2. */
+ * 3 = two-phase path (k >= 5 without tensor cores), 4 = scalar + rank-one form (2 * 2^k MACs per group); lone
+ * k <= 3 gates that take the direct kernel count as 2. */
 int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len) {
-  if (!plan || !out || out_len < 32) return fail("need 32 counters", 1);
-  memset(out, 0, 32 * sizeof(unsigned));
+  if (!plan || !out || out_len < 40) return fail("need 40 counters", 1);
+  memset(out, 0, 40 * sizeof(unsigned));
   for (const hq::PassInfo& pi : plan->plan.passes)
     for (uint32_t g = 0; g < pi.header.n_gates; ++g) {
       HqGateDesc gd;
@@ -544,8 +545,8 @@ int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len) {
       if (gd.k < 1 || gd.k > 8) continue;
       const bool fast = plan->plan.dtype == HQ_DTYPE_C64 && pi.header.max_k <= 3 && g < HQ_FAST_SLOTS &&
                         ((pi.header.fast_mask >> g) & 1u) && pi.header.n_gates > 1;
-      const unsigned a = fast ? 0u : (gd.kind == HQ_GATE_MMA ? 1u : (gd.kind == HQ_GATE_BIG ? 3u : 2u));
-      ++out[4 * (gd.k - 1) + a];
+      const unsigned a = fast ? 0u : (gd.kind == HQ_GATE_MMA ? 1u : (gd.kind == HQ_GATE_BIG ? 3u : (gd.kind == HQ_GATE_DR1 ? 4u : 2u)));
+      ++out[5 * (gd.k - 1) + a];
     }
   return 0;
 }

@@ -32,10 +32,15 @@
 #define HQ_GATE_ROWPAIR 2     // complex128 k = 2, 3: row-pair scheme (see HqGateDesc::tbl_rthread)
 #define HQ_GATE_MMA 3         // tensor-core path (hq_mma.cuh): mma.sync 3xTF32 / FP64, 2 <= k <= HQ_MMA_MAX_K
 #define HQ_MMA_MAX_K 6
+#define HQ_GATE_DR1 4         // "scalar + rank one": U = lambda * 1 + u v^T, 3 <= k <= HQ_DR1_MAX_K (hq_tile.cuh gate_dr1):
+                              // what a depolarizing channel is as a super-operator (hybridq/noise/channel/channel.py:413-529
+                              // build the dense 4^k x 4^k matrix; here it costs 2 * 2^k MACs per group instead of 4^k)
+#define HQ_DR1_MAX_K 4
 
 #define HQ_MAX_PER_THREAD 16   // units per thread per tile = 2^(unit bits - 8) <= 16
 #define HQ_MAX_PASS_GATES 24   // kernel matrices per pass after merging
-#define HQ_FAST_SLOTS 8        // constant-bank gate slots per pass (complex64, k <= 3)
+#define HQ_FAST_SLOTS 8        // constant-bank gate slots per pass (complex64, k <= 3); 12 measured 6 % slower on the
+                               // bench circuit (code size / register allocation of the slot switch), profiles/r02
 #define HQ_FAST_MAX_K 3
 
 struct HqGateDesc {        // 1280 bytes, lives in the device program buffer (read through L1)
@@ -45,6 +50,7 @@ struct HqGateDesc {        // 1280 bytes, lives in the device program buffer (re
                            //   small: row-major 2^k x 2^k, interleaved (re, im)
                            //   big  : column-major (transposed), interleaved
                            //   mma  : per-lane B fragments, 16 bytes each: [(s * KS + j) * 32 + lane]
+                           //   dr1  : lambda, u[2^k], v[2^k], interleaved (re, im)
   uint32_t n_free;         // number of entries in q[]
   uint8_t tpos[16];        // ascending LOCAL amplitude-bit positions of matrix bits 0..k-1
   uint8_t q[16];           // small: ordering of the non-target local UNIT bits (work-item bit b
@@ -102,5 +108,5 @@ struct HqPassHeader {      // passed to the kernel by value (constant bank)
 };
 
 static_assert(sizeof(HqGateDesc) == 624 + 96 + 512 + 32 + 16, "HqGateDesc layout");
-static_assert(sizeof(HqPassHeader) == 256 + 8 + HQ_FAST_SLOTS + 4 * 128 * HQ_FAST_SLOTS, "HqPassHeader layout");
+static_assert(sizeof(HqPassHeader) == 256 + 8 + ((HQ_FAST_SLOTS + 7) & ~7) + 4 * 128 * HQ_FAST_SLOTS, "HqPassHeader layout");
 static_assert(sizeof(HqPassHeader) + 256 <= 32764, "the pass header travels as a kernel parameter (large-parameter limit)");

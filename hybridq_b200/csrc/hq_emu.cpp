@@ -201,6 +201,8 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
       const HqGateDesc* g = gates + gi;
       if (V == 1 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
         for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
+      } else if (g->kind == HQ_GATE_DR1) {
+        for (int tid = 0; tid < HQ_THREADS; ++tid) hq::gate_dr1_dispatch(tile.data(), g, g->k, prog, g->mat_off, Tu, tid);
       } else if (g->kind == HQ_GATE_MMA) {
         emu_mma_gate(tile.data(), g, prog);
       } else if (V == 0 && g->kind == HQ_GATE_ROWPAIR) {

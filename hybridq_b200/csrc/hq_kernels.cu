@@ -195,6 +195,8 @@ __device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g,
                                                 const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
   if (kind == HQ_GATE_MMA) {
     gate_mma_dispatch<MMAK>(tile, g, k, prog, tid);
+  } else if (kind == HQ_GATE_DR1) {
+    if (MAXK >= 3) gate_dr1_dispatch(tile, g, k, prog, mat_off, Tu, tid);     // scalar + rank one (k = 3, 4)
   } else if (IsF64Unit<Unit>::value && kind == HQ_GATE_ROWPAIR) {
     rowpair_dispatch<MAXK>(tile, g, k, prog, mat_off, Tu, tid);
   } else {
@@ -340,7 +342,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     }
     __syncthreads();
 
-    apply_pass_gates<T, KCLASS, (NBUF == 1)>(tile, gates, ph, prog, Tbits, Tu, tid, CtaSync());
+    apply_pass_gates<T, KCLASS, true>(tile, gates, ph, prog, Tbits, Tu, tid, CtaSync());
 
     // drain
     if (!ph.has_perm) {

@@ -45,7 +45,69 @@ struct Canon {               // gate with ascending positions and accordingly pe
   unsigned k;
   std::vector<unsigned> pos;
   std::vector<std::complex<double>> U;
+  // "scalar + rank one" form U = lambda * 1 + u v^T (detect_dr1), e.g. a depolarizing channel as a super-operator
+  bool dr1 = false;
+  std::complex<double> lambda;
+  std::vector<std::complex<double>> u, v;
 };
+
+// Is U = lambda * 1 + u v^T?  u and v are read off the row and the column of the largest OFF-diagonal entry
+// (scale: u[i0] = 1), their two missing components off a second row / column, lambda = U_ii - u_i v_i must then be
+// the same for every i, and every entry is checked against the reconstruction.  Only worth it from k = 3 up.
+// Tolerance: the reconstruction must reproduce every entry to within what the kernel's own storage of the matrix
+// would lose anyway -- a few fp32 ulps of the largest entry for complex64 plans (so channels whose matrices were
+// built in single precision are still recognised), 1e-12 relative for complex128.
+bool detect_dr1(Canon& c, int dtype) {
+  c.dr1 = false;
+  if (c.k < 3 || c.k > HQ_DR1_MAX_K) return false;
+  const size_t dim = size_t(1) << c.k;
+  const std::vector<std::complex<double>>& U = c.U;
+  double scale = 0;
+  for (const auto& x : U) scale = std::max(scale, std::abs(x));
+  if (scale == 0) return false;
+  const double tol = (dtype == HQ_DTYPE_C64 ? 6e-8 : 1e-12) * scale;
+  size_t i0 = 0, j0 = 0;
+  double big = 0;
+  for (size_t i = 0; i < dim; ++i)
+    for (size_t j = 0; j < dim; ++j)
+      if (i != j && std::abs(U[i * dim + j]) > big) { big = std::abs(U[i * dim + j]); i0 = i; j0 = j; }
+  std::vector<std::complex<double>> u(dim, 0.0), v(dim, 0.0);
+  if (big > tol) {
+    u[i0] = 1.0;
+    for (size_t j = 0; j < dim; ++j)
+      if (j != i0) v[j] = U[i0 * dim + j];
+    for (size_t i = 0; i < dim; ++i)
+      if (i != j0 && i != i0) u[i] = U[i * dim + j0] / v[j0];
+    // u[j0] from another column, v[i0] from another row (the largest usable ones)
+    size_t j1 = dim, i1 = dim;
+    for (size_t j = 0; j < dim; ++j)
+      if (j != j0 && j != i0 && (j1 == dim || std::abs(v[j]) > std::abs(v[j1]))) j1 = j;
+    for (size_t i = 0; i < dim; ++i)
+      if (i != i0 && i != j0 && (i1 == dim || std::abs(u[i]) > std::abs(u[i1]))) i1 = i;
+    if (j1 == dim || i1 == dim) return false;
+    if (std::abs(v[j1]) > tol) u[j0] = U[j0 * dim + j1] / v[j1];
+    else {
+      for (size_t j = 0; j < dim; ++j)
+        if (j != j0 && std::abs(U[j0 * dim + j]) > tol) return false;      // row j0 has entries a zero u[j0] cannot make
+    }
+    if (std::abs(u[i1]) > tol) v[i0] = U[i1 * dim + i0] / u[i1];
+    else {
+      for (size_t i = 0; i < dim; ++i)
+        if (i != i0 && std::abs(U[i * dim + i0]) > tol) return false;
+    }
+  }
+  const std::complex<double> lam = U[0] - u[0] * v[0];
+  for (size_t i = 0; i < dim; ++i)
+    for (size_t j = 0; j < dim; ++j) {
+      const std::complex<double> want = u[i] * v[j] + (i == j ? lam : std::complex<double>(0, 0));
+      if (std::abs(U[i * dim + j] - want) > 8 * tol) return false;
+    }
+  c.dr1 = true;
+  c.lambda = lam;
+  c.u.swap(u);
+  c.v.swap(v);
+  return true;
+}
 
 bool canonicalise(const GateIn& g, unsigned n, Canon& out, std::string& err) {
   const unsigned k = g.k;
@@ -352,6 +414,20 @@ std::vector<std::complex<double>> embed(const Canon& c, const std::vector<unsign
   return out;
 }
 
+template <typename T>
+void write_dr1(std::vector<unsigned char>& prog, size_t off, const Canon& c) {
+  T* out = reinterpret_cast<T*>(prog.data() + off);
+  const size_t dim = size_t(1) << c.k;
+  out[0] = T(c.lambda.real());
+  out[1] = T(c.lambda.imag());
+  for (size_t i = 0; i < dim; ++i) {
+    out[2 + 2 * i] = T(c.u[i].real());
+    out[2 + 2 * i + 1] = T(c.u[i].imag());
+    out[2 + 2 * dim + 2 * i] = T(c.v[i].real());
+    out[2 + 2 * dim + 2 * i + 1] = T(c.v[i].imag());
+  }
+}
+
 // first := second * first on the union of their positions (second is applied after first).
 void merge_into(Canon& first, const Canon& second) {
   std::vector<unsigned> pos_u = first.pos;
@@ -370,6 +446,7 @@ void merge_into(Canon& first, const Canon& second) {
   first.k = unsigned(pos_u.size());
   first.pos = pos_u;
   first.U.swap(C);
+  first.dr1 = false;
 }
 
 struct Cluster {
@@ -407,11 +484,12 @@ std::vector<Cluster> merge_pass(const std::vector<Canon>& canon, const std::vect
     uint64_t gm = 0;
     for (unsigned p : g.pos) gm |= uint64_t(1) << p;
     int target = -1;
-    if (max_k > 0 && int(g.k) <= max_k) {
+    // a scalar + rank-one gate is cheaper on its own than anything it could be multiplied into
+    if (max_k > 0 && int(g.k) <= max_k && !g.dr1) {
       int best_gain = -1;
       for (int c = int(cl.size()) - 1; c >= 0; --c) {
         const int ku = union_k(cl[size_t(c)].mask, gm);
-        if (ku <= max_k && ku <= HQ_SMALL_K) {
+        if (ku <= max_k && ku <= HQ_SMALL_K && !cl[size_t(c)].gate.dr1) {
           // a merged matrix that costs up to HQ_MERGE_SLACK % more than its two parts is still taken: the merge
           // is pairwise and greedy, and a cluster that has grown to k bits absorbs every later gate on those
           // bits for free (a triangle of k = 2 gates becomes ONE k = 3 matrix only if the first pair may merge)
@@ -474,6 +552,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     if (!canonicalise(gates_in[i], n, c, plan.error)) return 1;
     std::vector<unsigned> b = c.pos;
     if (choose_run_bits(b, T, hard_min_run) < 0) { plan.error = "gate does not fit in a tile"; return 1; }
+    detect_dr1(c, dtype);
     canon.push_back(std::move(c));
     canon_id.push_back(unsigned(i));
   }
@@ -531,7 +610,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   const int merge_pass_cost = opts.merge_pass_cost;
   std::vector<std::vector<Cluster>> merged(drafts.size());
   std::vector<PassInfo> infos(drafts.size());
-  struct GateLayout { bool mma = false; MmaLayout L; uint8_t tpos[16] = {0}; size_t bytes = 0; };
+  struct GateLayout { bool mma = false; bool dr1 = false; MmaLayout L; uint8_t tpos[16] = {0}; size_t bytes = 0; };
   std::vector<std::vector<GateLayout>> layouts(drafts.size());
   size_t total_gates = 0;
   size_t mat_bytes = 0;
@@ -576,9 +655,11 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       }
       // a lone k <= 3 gate keeps its plain matrix: such passes go to the direct kernel (hq_abi.cu)
       const bool lone_small = merged[d].size() == 1 && c.k <= 3;
-      gl.mma = mma_on && !lone_small && int(c.k) >= mma_min_k && int(c.k) <= HQ_MMA_MAX_K &&
+      gl.dr1 = c.dr1 && !lone_small;
+      gl.mma = !gl.dr1 && mma_on && !lone_small && int(c.k) >= mma_min_k && int(c.k) <= HQ_MMA_MAX_K &&
                mma_layout(gl.tpos, int(c.k), Tbits, V, gl.L);
-      gl.bytes = gl.mma ? mma_frag_bytes(c.k) : (((esz << (2 * c.k)) + 15) & ~size_t(15));
+      gl.bytes = gl.dr1 ? (((esz * (1 + (size_t(2) << c.k))) + 15) & ~size_t(15))
+                        : (gl.mma ? mma_frag_bytes(c.k) : (((esz << (2 * c.k)) + 15) & ~size_t(15)));
       mat_bytes += gl.bytes;
     }
   }
@@ -603,7 +684,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       HqGateDesc gd;
       memset(&gd, 0, sizeof(gd));
       gd.k = c.k;
-      gd.kind = gl.mma ? HQ_GATE_MMA : (c.k <= HQ_SMALL_K ? HQ_GATE_SMALL : HQ_GATE_BIG);
+      gd.kind = gl.dr1 ? HQ_GATE_DR1 : (gl.mma ? HQ_GATE_MMA : (c.k <= HQ_SMALL_K ? HQ_GATE_SMALL : HQ_GATE_BIG));
       gd.mat_off = uint32_t(mat_cursor);
       std::vector<bool> is_t;
       is_t.assign(size_t(Tbits), false);
@@ -613,7 +694,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       }
       // canonical positions are ascending globally, hence ascending locally too
       std::vector<unsigned> free_bits;
-      if (gd.kind == HQ_GATE_SMALL) {
+      if (gd.kind == HQ_GATE_SMALL || gd.kind == HQ_GATE_DR1) {
         for (int u = 0; u < Tu; ++u)
           if (!is_t[size_t(u + V)]) free_bits.push_back(unsigned(u));
         free_bits = lane_order(free_bits);
@@ -623,14 +704,17 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       }
       gd.n_free = uint32_t(free_bits.size());
       for (size_t i = 0; i < free_bits.size() && i < 16; ++i) gd.q[i] = uint8_t(free_bits[i]);
-      if (gd.kind == HQ_GATE_SMALL) make_lane_tables(gd, Tu, V);
+      if (gd.kind == HQ_GATE_SMALL || gd.kind == HQ_GATE_DR1) make_lane_tables(gd, Tu, V);
       if (gd.kind == HQ_GATE_MMA) make_mma_tables(gd, gl.L, V);
       if (gd.kind == HQ_GATE_SMALL && dtype == HQ_DTYPE_C128 && opts.fast_slots != 0 && (gd.k == 2 || gd.k == 3)) {
         make_rowpair_tables(gd, Tu);
         gd.kind = HQ_GATE_ROWPAIR;
       }
       memcpy(plan.program.data() + gate_cursor * sizeof(HqGateDesc), &gd, sizeof(gd));
-      if (gd.kind == HQ_GATE_MMA)
+      if (gd.kind == HQ_GATE_DR1) {
+        if (dtype == HQ_DTYPE_C64) write_dr1<float>(plan.program, mat_cursor, c);
+        else write_dr1<double>(plan.program, mat_cursor, c);
+      } else if (gd.kind == HQ_GATE_MMA)
         write_mma_fragments(plan.program, mat_cursor, c, gl.L, dtype);
       else if (dtype == HQ_DTYPE_C64)
         write_matrix<float>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
@@ -648,7 +732,8 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         }
       }
       for (unsigned id : cluster.ids) pi.gate_ids.push_back(canon_id[id]);
-      pi.header.max_k = std::max<uint32_t>(pi.header.max_k, c.k);
+      // kernel class: a scalar + rank-one gate needs the registers of a k = 3 pass, not of a k = 4 one
+      pi.header.max_k = std::max<uint32_t>(pi.header.max_k, gd.kind == HQ_GATE_DR1 ? 3u : c.k);
     }
     plan.passes.push_back(std::move(pi));
   }

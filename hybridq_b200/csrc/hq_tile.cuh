@@ -659,6 +659,122 @@ HQ_DEV void gate_big_phaseB(typename Traits<T>::Cplx* tile, const HqGateDesc& g,
 }
 
 // ---------------------------------------------------------------------------------------
+// "scalar + rank one" gates (HQ_GATE_DR1): psi' = lambda psi + u (v . psi) on every group of 2^k amplitudes.
+// Same lane tables and work-item layout as the register path; `p` = [lambda, u[2^k], v[2^k]] (complex).
+// A thread first reduces v . psi over its group(s), then rescales and adds: 2 * 2^k complex MACs per group.
+// ---------------------------------------------------------------------------------------
+template <typename R>
+HQ_DEV void cmul_add(R& ar, R& ai, R ur, R ui, R xr, R xi) { cmac(ar, ai, ur, ui, xr, xi); }
+
+// Register-light on purpose (two sweeps over the group's units, nothing but the two dot products live between
+// them): the gate shares a kernel with the FFMA2 slots and must not push their accumulators out of registers; the
+// second read of the units costs half a shared-memory round trip.
+template <int KK, bool LOW>
+HQ_DEV void gate_dr1_f32(float4* tile, const HqGateDesc* __restrict__ g, const float2* __restrict__ p, int Tu, int tid) {
+  const int UD = 1 << KK;
+  const int DIM = LOW ? 2 * UD : UD;
+  const int nq = Tu - KK;
+  const uint32_t nwork = 1u << nq;
+  if (uint32_t(tid) >= nwork) return;
+  const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
+  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  const IterBasis ib = load_iter_basis(g->tbl_iter);
+  const float2 lam = HQ_LDG(&p[0]);
+  const float2* __restrict__ u = p + 1;
+  const float2* __restrict__ v = p + 1 + DIM;
+  HQ_NOUNROLL
+  for (uint32_t it = 0; it < niter; ++it) {
+    const uint32_t sb = st ^ iter_offset(ib, it);
+    float d0r = 0.f, d0i = 0.f, d1r = 0.f, d1i = 0.f;      // v . psi of the even / odd group (or of the one group)
+    HQ_UNROLL
+    for (int m = 0; m < UD; ++m) {
+      const float4 x = tile[sb ^ uint32_t(HQ_LDG(&g->tbl_x[m]))];
+      if (!LOW) {
+        const float2 vj = HQ_LDG(&v[m]);
+        cmac(d0r, d0i, vj.x, vj.y, x.x, x.y);
+        cmac(d1r, d1i, vj.x, vj.y, x.z, x.w);
+      } else {
+        const float2 va = HQ_LDG(&v[2 * m]), vb = HQ_LDG(&v[2 * m + 1]);
+        cmac(d0r, d0i, va.x, va.y, x.x, x.y);
+        cmac(d0r, d0i, vb.x, vb.y, x.z, x.w);
+      }
+    }
+    HQ_UNROLL
+    for (int m = 0; m < UD; ++m) {
+      const uint32_t slot = sb ^ uint32_t(HQ_LDG(&g->tbl_x[m]));
+      const float4 x = tile[slot];
+      float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+      cmac(ar, ai, lam.x, lam.y, x.x, x.y);
+      cmac(br, bi, lam.x, lam.y, x.z, x.w);
+      if (!LOW) {
+        const float2 ui = HQ_LDG(&u[m]);
+        cmac(ar, ai, ui.x, ui.y, d0r, d0i);
+        cmac(br, bi, ui.x, ui.y, d1r, d1i);
+      } else {
+        const float2 ua = HQ_LDG(&u[2 * m]), ub = HQ_LDG(&u[2 * m + 1]);
+        cmac(ar, ai, ua.x, ua.y, d0r, d0i);
+        cmac(br, bi, ub.x, ub.y, d0r, d0i);
+      }
+      tile[slot] = make_float4(ar, ai, br, bi);
+    }
+  }
+}
+
+template <int KK>
+HQ_DEV void gate_dr1_f64(double2* tile, const HqGateDesc* __restrict__ g, const double2* __restrict__ p, int Tu, int tid) {
+  const int DIM = 1 << KK;
+  const int nq = Tu - KK;
+  const uint32_t nwork = 1u << nq;
+  if (uint32_t(tid) >= nwork) return;
+  const uint32_t niter = nq > HQ_THREADS_LOG2 ? (nwork >> HQ_THREADS_LOG2) : 1u;
+  const uint32_t st = HQ_LDG(&g->tbl_thread[tid]);
+  const IterBasis ib = load_iter_basis(g->tbl_iter);
+  const double2 lam = HQ_LDG(&p[0]);
+  const double2* __restrict__ u = p + 1;
+  const double2* __restrict__ v = p + 1 + DIM;
+  HQ_NOUNROLL
+  for (uint32_t it = 0; it < niter; ++it) {
+    const uint32_t sb = st ^ iter_offset(ib, it);
+    double dr = 0., di = 0.;
+    HQ_UNROLL
+    for (int m = 0; m < DIM; ++m) {
+      const double2 x = tile[sb ^ uint32_t(HQ_LDG(&g->tbl_x[m]))];
+      const double2 vj = HQ_LDG(&v[m]);
+      cmac(dr, di, vj.x, vj.y, x.x, x.y);
+    }
+    HQ_UNROLL
+    for (int m = 0; m < DIM; ++m) {
+      const uint32_t slot = sb ^ uint32_t(HQ_LDG(&g->tbl_x[m]));
+      const double2 x = tile[slot];
+      double ar = 0., ai = 0.;
+      const double2 ui = HQ_LDG(&u[m]);
+      cmac(ar, ai, lam.x, lam.y, x.x, x.y);
+      cmac(ar, ai, ui.x, ui.y, dr, di);
+      tile[slot] = make_double2(ar, ai);
+    }
+  }
+}
+
+HQ_DEV void gate_dr1_dispatch(float4* tile, const HqGateDesc* g, uint32_t k, const unsigned char* prog, uint32_t mat_off,
+                              int Tu, int tid) {
+  const float2* p = reinterpret_cast<const float2*>(prog + mat_off);
+  const bool low = HQ_LDG(&g->tpos[0]) == 0;
+  if (!low) {
+    if (k == 3) gate_dr1_f32<3, false>(tile, g, p, Tu, tid);
+    else if (k == 4) gate_dr1_f32<4, false>(tile, g, p, Tu, tid);
+  } else {
+    if (k == 3) gate_dr1_f32<2, true>(tile, g, p, Tu, tid);
+    else if (k == 4) gate_dr1_f32<3, true>(tile, g, p, Tu, tid);
+  }
+}
+HQ_DEV void gate_dr1_dispatch(double2* tile, const HqGateDesc* g, uint32_t k, const unsigned char* prog, uint32_t mat_off,
+                              int Tu, int tid) {
+  const double2* p = reinterpret_cast<const double2*>(prog + mat_off);
+  if (k == 3) gate_dr1_f64<3>(tile, g, p, Tu, tid);
+  else if (k == 4) gate_dr1_f64<4>(tile, g, p, Tu, tid);
+}
+
+// ---------------------------------------------------------------------------------------
 // dispatch of one register-path gate
 // ---------------------------------------------------------------------------------------
 // MAXK prunes the switch so that a pass made of small gates only is compiled with few

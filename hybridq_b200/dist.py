@@ -471,6 +471,21 @@ class ShardedRunner:
             factor *= {"0": (1, 0), "1": (0, 1), "+": (r, r), "-": (r, -r)}[spec[j]][bit]
         self.engine.init_product(self.a, spec[self.g:], factor)
 
+    def dump(self, path, **kw):
+        """Sharded checkpoint: every rank writes `path.rank<r>of<w>` (+ .json) with its shard in canonical order
+        (DeviceState.dump: chunked through pinned memory, so 64 GiB shards do not need 64 GiB of host RAM)."""
+        if any(w != i for i, w in enumerate(self.final_where)):
+            raise RuntimeError("dump() needs the canonical bit order (plan with restore=True)")
+        self.a.dump(f"{path}.rank{self.rank}of{self.world}",
+                    meta={"rank": self.rank, "world": self.world, "n_qubits_global": self.n}, **kw)
+        self.dist.barrier()
+
+    def load(self, path, **kw):
+        """Read a checkpoint written by :meth:`dump` with the same number of ranks."""
+        self.a.load(f"{path}.rank{self.rank}of{self.world}",
+                    expect={"rank": self.rank, "world": self.world, "n_qubits_global": self.n}, **kw)
+        self.dist.barrier()
+
     def load_shard(self, host_shard):
         self.engine.upload(self.a, host_shard)
 

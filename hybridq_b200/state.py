@@ -94,12 +94,12 @@ class Plan:
     def arithmetic(self) -> dict:
         """{'k2': {'ffma2_slots': .., 'tensor_cores': .., 'fma_generic': .., 'two_phase': ..}, ...}: how many
         kernel matrices of each size run on which arithmetic (hq_plan_arith_counts)."""
-        out = (ctypes.c_uint32 * 32)()
-        check(lib.hq_plan_arith_counts(self._h, out, 32), "hq_plan_arith_counts")
-        names = ("ffma2_slots", "tensor_cores", "fma_generic", "two_phase")
+        out = (ctypes.c_uint32 * 40)()
+        check(lib.hq_plan_arith_counts(self._h, out, 40), "hq_plan_arith_counts")
+        names = ("ffma2_slots", "tensor_cores", "fma_generic", "two_phase", "scalar_plus_rank_one")
         res = {}
         for k in range(1, 9):
-            row = {names[a]: int(out[4 * (k - 1) + a]) for a in range(4) if out[4 * (k - 1) + a]}
+            row = {names[a]: int(out[5 * (k - 1) + a]) for a in range(5) if out[5 * (k - 1) + a]}
             if row:
                 res[f"k{k}"] = row
         return res
@@ -340,6 +340,88 @@ class DeviceState:
         check(lib.hq_scale_dev(self.ptr, self.dtype, self.n_amps, float(factor), _stream_handle(stream, self.device)),
               "hq_scale_dev")
         return self
+
+    # -- checkpoint / sampling ----------------------------------------------------------
+    @_dev
+    def dump(self, path, chunk_bytes: int = 1 << 28, meta: dict | None = None) -> None:
+        """Write the state to `path` (raw little-endian interleaved complex, preceded by nothing) plus
+        `path + '.json'` describing it; the copy goes through a pinned staging buffer chunk by chunk, so a state
+        larger than host RAM can be checkpointed.  The reference has no checkpointing."""
+        import json
+        import torch
+        from pathlib import Path
+        path = Path(path)
+        n_chunk = max(1, min(self.nbytes, int(chunk_bytes)) // self.complex_type.itemsize)
+        stage = torch.empty(n_chunk, dtype=_torch_ctype(self.complex_type), pin_memory=True)
+        host = stage.numpy()
+        s = _stream_handle(None, self.device)
+        with open(path, "wb") as f, _on(self.device):
+            for a in range(0, self.n_amps, n_chunk):
+                m = min(n_chunk, self.n_amps - a)
+                check(lib.hq_memcpy_d2h(ctypes.c_void_p(host.ctypes.data),
+                                        ctypes.c_void_p(self.tensor.data_ptr() + a * self.complex_type.itemsize),
+                                        m * self.complex_type.itemsize, s), "d2h")
+                check(lib.hq_stream_sync(s), "sync")
+                f.write(memoryview(host[:m]))
+        info = {"format": "hybridq_b200 state v1", "n_qubits": self.n_qubits, "complex_type": str(self.complex_type),
+                "n_amps": self.n_amps, "layout": "interleaved complex, index bit 0 = LSB, first sorted qubit = MSB"}
+        info.update(meta or {})
+        Path(str(path) + ".json").write_text(json.dumps(info))
+
+    @_dev
+    def load(self, path, chunk_bytes: int = 1 << 28, expect: dict | None = None) -> "DeviceState":
+        """Read a state written by :meth:`dump` (sizes, precision and any `expect`ed metadata must match)."""
+        import json
+        import torch
+        from pathlib import Path
+        path = Path(path)
+        info = json.loads(Path(str(path) + ".json").read_text())
+        want = {"n_qubits": self.n_qubits, "complex_type": str(self.complex_type)}
+        want.update(expect or {})
+        for k, v in want.items():
+            if info.get(k) != v:
+                raise ValueError(f"checkpoint {path}: {k} = {info.get(k)!r}, expected {v!r}")
+        if path.stat().st_size != self.nbytes:
+            raise ValueError(f"checkpoint {path}: {path.stat().st_size} bytes, expected {self.nbytes}")
+        n_chunk = max(1, min(self.nbytes, int(chunk_bytes)) // self.complex_type.itemsize)
+        stage = torch.empty(n_chunk, dtype=_torch_ctype(self.complex_type), pin_memory=True)
+        host = stage.numpy()
+        s = _stream_handle(None, self.device)
+        with open(path, "rb") as f, _on(self.device):
+            for a in range(0, self.n_amps, n_chunk):
+                m = min(n_chunk, self.n_amps - a)
+                f.readinto(memoryview(host[:m]).cast("B"))
+                check(lib.hq_memcpy_h2d(ctypes.c_void_p(self.tensor.data_ptr() + a * self.complex_type.itemsize),
+                                        ctypes.c_void_p(host.ctypes.data), m * self.complex_type.itemsize, s), "h2d")
+                check(lib.hq_stream_sync(s), "sync")
+        return self
+
+    @_dev
+    def sample(self, n_samples: int, seed=None, block_bits: int = 16) -> np.ndarray:
+        """Draw `n_samples` basis-state indices from |psi|^2 WITHOUT collapsing the state (int64 array; bit b of
+        an index = index bit b, i.e. `format(i, f'0{n}b')` reads first sorted qubit first).  Two levels: one
+        device reduction gives the probability of every block of 2^block_bits consecutive amplitudes (the
+        marginal of the high index bits), the block of each sample is drawn on the host, and only the drawn
+        blocks are copied back to finish the draw inside them."""
+        rng = np.random.default_rng(seed)
+        n = self.n_qubits
+        B = min(n, max(int(block_bits), n - MARGINAL_MAX_K))
+        hi = list(range(B, n))
+        p_blocks = self.marginal(hi).sum(axis=1) if hi else np.array([self.norm2()])
+        p_blocks = p_blocks / p_blocks.sum()
+        blocks = rng.choice(len(p_blocks), size=int(n_samples), p=p_blocks)
+        out = np.empty(int(n_samples), dtype=np.int64)
+        buf = np.empty(2 ** B, dtype=self.complex_type)
+        s = _stream_handle(None, self.device)
+        for blk in np.unique(blocks):
+            check(lib.hq_memcpy_d2h(ctypes.c_void_p(buf.ctypes.data),
+                                    ctypes.c_void_p(self.tensor.data_ptr() + int(blk) * (2 ** B) * self.complex_type.itemsize),
+                                    buf.nbytes, s), "d2h")
+            check(lib.hq_stream_sync(s), "sync")
+            p = buf.real.astype(np.float64) ** 2 + buf.imag.astype(np.float64) ** 2
+            sel = np.flatnonzero(blocks == blk)
+            out[sel] = (int(blk) << B) | rng.choice(2 ** B, size=sel.size, p=p / p.sum())
+        return out
 
     def copy(self) -> "DeviceState":
         return DeviceState(self.n_qubits, self.complex_type, self.device, tensor=self.tensor.clone())

@@ -181,9 +181,9 @@ int hq_plan_pass_gates(const hq_plan* plan, int pass, unsigned int* out, int out
 int hq_plan_run(hq_plan* plan, void* state, void* stream);
 /* launch passes [first, last) only */
 int hq_plan_run_range(hq_plan* plan, void* state, int first, int last, void* stream);
-/* which arithmetic the kernel matrices of a plan run on: out[4 * (k - 1) + a], k = 1..8, a = 0 constant-bank FFMA2
- * slot, 1 tensor cores (mma.sync 3xTF32 / FP64), 2 generic FMA path (incl. the direct kernel), 3 two-phase path;
- * out has 32 entries */
+/* which arithmetic the kernel matrices of a plan run on: out[5 * (k - 1) + a], k = 1..8, a = 0 constant-bank FFMA2
+ * slot, 1 tensor cores (mma.sync 3xTF32 / FP64), 2 generic FMA path (incl. the direct kernel), 3 two-phase path,
+ * 4 scalar + rank-one form (a depolarizing channel's super-operator: lambda * 1 + u v^T); out has 40 entries */
 int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len);
 
 /* ---- multi-GPU: rank-bit <-> local-bit exchange fused into a pass (no reference counterpart: the reference's

@@ -44,12 +44,25 @@ def main():
         print(f"sharded x{world} vs 1 GPU, n={n}: max-abs diff {err:.3e}; {runner.describe()}", flush=True)
         ok = err <= 1e-6
         del st
+    # sharded checkpoint: dump, clobber, load -> the gathered state is unchanged (bit-exact)
+    import tempfile
+    ckpt = os.path.join(tempfile.gettempdir(), f"hq_ckpt_test_{os.environ.get('MASTER_PORT', '0')}")
+    runner.dump(ckpt, chunk_bytes=1 << 24)
+    runner.a.tensor.zero_()
+    runner.load(ckpt, chunk_bytes=1 << 24)
+    ok_ckpt = bool(np.array_equal(runner.gather(), out))
+    ok = ok and ok_ckpt
+    for f in (f"{ckpt}.rank{rank}of{world}", f"{ckpt}.rank{rank}of{world}.json"):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
     # the public entry point on the same circuit: every rank passes the full initial state, gets its shard back
     shard = hb.simulate(gates, initial_state=psi0.reshape((2,) * n), complex_type=ctype, shard=True)
     nl = n - int(round(np.log2(world)))
     mine = out[rank * 2 ** nl:(rank + 1) * 2 ** nl]
     err2 = float(np.abs(shard.reshape(-1) - mine).max())
-    flag = torch.tensor([1 if (ok and err2 <= 1e-6) else 0], device="cuda")
+    flag = torch.tensor([1 if (ok and ok_ckpt and err2 <= 1e-6) else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"simulate(shard=True) vs ShardedRunner: max-abs diff {err2:.3e}", flush=True)

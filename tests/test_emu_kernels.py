@@ -121,3 +121,32 @@ def test_planner_properties(emu):
                             assert bit < L or bit in p["high_pos"]
                 if opts and opts[2] == 0:
                     assert all(p["n_gates"] == 1 for p in passes)
+
+
+def test_scalar_plus_rank_one_gates(emu, oracle, c_oracle):
+    """HQ_GATE_DR1: a super-operator of the form lambda * 1 + u v^T -- what the reference's dense
+    depolarizing channel matrices are (hybridq/noise/channel/channel.py:413-529) -- is detected by the planner and
+    applied with 2 * 2^k MACs per group; k = 3, 4, with and without a target on amplitude bit 0, both precisions."""
+    import hybridq_b200 as hb
+    rng = np.random.default_rng(9)
+    paulis = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]])]
+    depol2 = sum(((1 - 0.01) if a == b == 0 else 0.01 / 15) * np.kron(np.kron(paulis[a], paulis[b]), np.kron(paulis[a], paulis[b]).conj())
+                 for a in range(4) for b in range(4))
+    u, v = rng.standard_normal(8) + 1j * rng.standard_normal(8), rng.standard_normal(8) + 1j * rng.standard_normal(8)
+    generic3 = (0.9 + 0.1j) * np.eye(8) + 0.05 * np.outer(u, v)
+    n = 12
+    for ctype, tol in (("complex64", 1e-6), ("complex128", 1e-14)):
+        for U in (depol2, generic3):
+            k = int(np.log2(U.shape[0]))
+            for pos in ([0, 3, 5, 9][:k], [2, 4, 7, 11][:k], [11, 1, 6, 3][:k]):
+                psi = _rand_state(rng, n, ctype)
+                other = (rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))) / 4
+                gates = [(other, [1, 8]), (U, pos), (other.T, [8, 10])]
+                ref = oracle.evolve_oracle(psi, [(g.astype(ctype), p) for g, p in gates], c_oracle)
+                out, n_pass, _ = emu.run(psi, gates, None)
+                assert np.abs(out - ref).max() < tol, (ctype, k, pos)
+                plan = hb.Plan(gates, n, ctype)
+                assert plan.arithmetic()[f"k{k}"].get("scalar_plus_rank_one") == 1, plan.arithmetic()
+    # a dense Haar matrix is not of that form
+    from hybridq_b200.circuits import haar_unitary
+    assert "scalar_plus_rank_one" not in str(hb.Plan([(haar_unitary(16, rng), [1, 3, 5, 7]), (other, [2, 9])], n, "complex64").arithmetic())

@@ -413,3 +413,35 @@ def test_state_on_a_device_that_is_not_current(hb, oracle, c_oracle):
     assert np.abs(st.download() - ref).max() <= TOL["complex64"]
     out = hb.simulate(matching_circuit(n, depth=4, seed=1), initial_state=psi0.reshape((2,) * n), device=1)
     assert np.abs(out.reshape(-1) - ref).max() <= TOL["complex64"]
+
+
+# ------------------------------------------------------------------ checkpoint and sampling
+def test_checkpoint_round_trip_and_sampling(hb, tmp_path):
+    """dump / load through a small pinned staging buffer (several chunks) is bit-exact; a checkpoint of another
+    size or precision is refused; sample() draws from |psi|^2 without touching the state."""
+    from hybridq_b200.circuits import matching_circuit
+    n = 18
+    st = hb.simulate(matching_circuit(n, depth=4, seed=18), initial_state="0" * n, complex_type="complex64",
+                     return_numpy_array=False)
+    ref = st.download()
+    st.dump(tmp_path / "ckpt.bin", chunk_bytes=1 << 18)
+    back = hb.DeviceState(n, "complex64").load(tmp_path / "ckpt.bin", chunk_bytes=3 << 17)
+    assert np.array_equal(back.download(), ref)
+    with pytest.raises(ValueError):
+        hb.DeviceState(n, "complex128").load(tmp_path / "ckpt.bin")
+    with pytest.raises(ValueError):
+        hb.DeviceState(n - 1, "complex64").load(tmp_path / "ckpt.bin")
+    # sampling: a state with three populated basis states of known weights
+    psi = np.zeros(2 ** n, dtype=np.complex64)
+    psi[5], psi[70000], psi[2 ** n - 1] = np.sqrt(0.5), 1j * np.sqrt(0.3), -np.sqrt(0.2)
+    st = hb.DeviceState(n, "complex64").upload(psi)
+    draws = st.sample(20000, seed=1, block_bits=10)
+    assert set(np.unique(draws)) == {5, 70000, 2 ** n - 1}
+    freq = np.array([(draws == i).mean() for i in (5, 70000, 2 ** n - 1)])
+    assert np.abs(freq - [0.5, 0.3, 0.2]).max() < 0.02
+    assert np.array_equal(st.download(), psi)              # not collapsed
+    # and of an evolved state: empirical distribution of the top 4 bits vs the exact marginal
+    draws = back.sample(50000, seed=2)
+    top = np.bincount(draws >> (n - 4), minlength=16) / 50000
+    want = back.marginal(list(range(n - 4, n))).sum(axis=1)
+    assert np.abs(top - want).max() < 0.02

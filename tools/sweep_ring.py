@@ -20,8 +20,19 @@ hb.lib.hq_set_tuning(-1, -1, 0)          # no direct kernel: m = 1 goes through 
 bits = [5, 6, 7, 8, 9, 10, 11, 12, 14, 17, 20, 23]
 
 
+_P = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]])]
+DEPOL2 = sum(((1 - 0.01) if a == b == 0 else 0.01 / 15) * np.kron(np.kron(_P[a], _P[b]), np.kron(_P[a], _P[b]).conj())
+             for a in range(4) for b in range(4))
+
+
 def gates_for(kind, m):
-    k = 2 if kind == "k2" else 3
+    if kind in ("dr1k4", "k4mma"):
+        out = []
+        for j in range(m):
+            pos = [bits[(4 * j + i) % 8] for i in range(4)]
+            out.append((DEPOL2 if kind == "dr1k4" else haar_unitary(16, rng), pos))
+        return out
+    k = 2 if kind in ("k2", "k2generic") else 3
     out = []
     for j in range(m):
         pos = [bits[(k * j + i) % len(bits)] for i in range(k)]
@@ -43,7 +54,8 @@ def time_plan(plan, reps=5):
 
 
 for kind, opts in (("k2", dict(merge_max_k=0)), ("k3mma", dict(merge_max_k=0, mma_min_k=3)),
-                   ("k3fast", dict(merge_max_k=0, mma_min_k=0)), ("k3generic", dict(merge_max_k=0, mma_min_k=0, fast_slots=0))):
+                   ("k3fast", dict(merge_max_k=0, mma_min_k=0)), ("k3generic", dict(merge_max_k=0, mma_min_k=0, fast_slots=0)),
+                   ("dr1k4", dict(merge_max_k=0)), ("k4mma", dict(merge_max_k=0)), ("k2generic", dict(merge_max_k=0, fast_slots=0))):
     for m in (1, 2, 3, 4, 6, 8):
         plan = hb.Plan(gates_for(kind, m), n, ctype, hb.PlanOptions(**opts))
         row = {"n": n, "ctype": ctype, "kind": kind, "m": m, "passes": plan.n_passes, "kernel_gates": plan.n_kernel_gates}
