@@ -561,6 +561,10 @@ int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_
   out[3] = ph.has_perm;
   out[4] = unsigned(plan->plan.passes[size_t(pass)].gate_ids.size());
   for (unsigned i = 0; i < ph.n_high; ++i) out[5 + i] = ph.high_pos[i];
+  if (out_len >= 7 + int(ph.n_high)) {        // optional tail: which gates sit on FFMA2 slots / are chained
+    out[5 + ph.n_high] = ph.fast_mask;
+    out[6 + ph.n_high] = ph.chain_mask;
+  }
   return 0;
 }
 int hq_plan_pass_gates(const hq_plan* plan, int pass, unsigned int* out, int out_len) {

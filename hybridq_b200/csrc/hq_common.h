@@ -102,7 +102,9 @@ struct HqPassHeader {      // passed to the kernel by value (constant bank)
   // uniform-register operand of an FFMA2: on B200 a 3-register FFMA issues at 21 TFMA/s, one with a
   // constant-bank operand at 35 TFMA/s (profiles/r01/microbench_fma.jsonl).
   uint32_t fast_mask;
-  uint32_t reserved2;
+  // bit s set: slot gates s and s + 1 belong to one warp-closed chain (hq_plan.cpp) -- every warp touches the same
+  // set of units in both, so only __syncwarp() separates them, not a CTA barrier
+  uint32_t chain_mask;
   uint8_t fast_k[HQ_FAST_SLOTS];
   float fast_u[HQ_FAST_SLOTS][2 << (2 * HQ_FAST_MAX_K)];
 };

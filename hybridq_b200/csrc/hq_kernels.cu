@@ -268,7 +268,8 @@ __device__ __forceinline__ void apply_pass_gates(typename Traits<T>::Unit* tile,
       gate_fast_slot<MAXK>(tile, sr, ph, gi, Tu, tid);       // complex64 k <= 3: constant-bank FFMA2
       // the next slot gate's addressing constants travel while this thread waits at the barrier
       if (gi + 1 < n_gates && gi + 1 < HQ_FAST_SLOTS && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
-      sync();
+      if ((ph.chain_mask >> gi) & 1u) __syncwarp();      // the next gate's warps work on the very same units
+      else sync();
       continue;
     }
     if (any_fast && gi + 1 < n_gates && gi + 1 < HQ_FAST_SLOTS && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);

@@ -21,6 +21,13 @@ int default_mma_min_k(int dtype) { return dtype == HQ_DTYPE_C64 ? 4 : 2; }
 
 namespace {
 
+// Warp-closed chains (see plan_build): measured on B200 in round 2 -- 105 of the bench circuit's 112 gate-to-gate
+// barriers become __syncwarp(), results identical, but no gain (128.1 vs 126.0 ms/step; a 2 x 4-gate pass 4.60 vs
+// 4.13 ms, profiles/r02/sweep_ring_g.jsonl): the CTA barrier is not what limits the gate loop.  Kept as a
+// compile-time experiment, off by default.
+#ifndef HQ_WARP_CHAINS
+#define HQ_WARP_CHAINS 0
+#endif
 #ifndef HQ_MERGE_SLACK
 #define HQ_MERGE_SLACK 10
 #endif
@@ -677,6 +684,49 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     pi.header.gates_off = uint32_t(gate_cursor * sizeof(HqGateDesc));
     const int Tbits = int(pi.header.tile_bits);
     const int Tu = Tbits - V;
+    // ---- warp-closed chains (complex64 FFMA2 slots): consecutive slot gates whose unit-level target bits
+    // leave at least three unit bits untouched by ALL of them get those three bits as the warp-index bits of
+    // their work-item maps.  The units a warp works on are then the same set for every gate of the chain, so
+    // __syncwarp() replaces the CTA barrier between them (HqPassHeader::chain_mask).
+    const size_t ng = merged[di].size();
+    std::vector<uint32_t> chain_w(ng, 0);          // mask of the three warp-index unit bits (0 = not chained)
+    std::vector<size_t> chain_first(ng, 0);
+#if HQ_WARP_CHAINS
+    if (dtype == HQ_DTYPE_C64 && opts.fast_slots != 0 && Tu >= HQ_THREADS_LOG2 + 3) {
+      auto slot_gate = [&](size_t ci, uint32_t& tmask) {
+        const Canon& c = merged[di][ci].gate;
+        const GateLayout& gl = layouts[di][ci];
+        if (ci >= HQ_FAST_SLOTS || gl.mma || gl.dr1 || c.k > HQ_FAST_MAX_K || (ng == 1 && c.k <= 3)) return false;
+        tmask = 0;
+        int kk = 0;
+        for (unsigned i = 0; i < c.k; ++i)
+          if (int(gl.tpos[i]) >= V) { tmask |= 1u << (gl.tpos[i] - V); ++kk; }
+        return Tu - kk >= HQ_THREADS_LOG2;          // at least one work item per thread
+      };
+      size_t a = 0;
+      while (a < ng) {
+        uint32_t un = 0;
+        if (!slot_gate(a, un)) { ++a; continue; }
+        size_t b = a + 1;
+        for (; b < ng; ++b) {
+          uint32_t tm = 0;
+          if (!slot_gate(b, tm)) break;
+          if (__builtin_popcount(un | tm) > Tu - 3) break;
+          un |= tm;
+        }
+        if (b - a >= 2) {
+          uint32_t w = 0;
+          int cnt = 0;
+          for (int u = Tu - 1; u >= 0 && cnt < 3; --u)
+            if (!((un >> u) & 1u)) { w |= 1u << u; ++cnt; }
+          for (size_t ci = a; ci < b; ++ci) { chain_w[ci] = w; chain_first[ci] = a; }
+        }
+        a = b;
+      }
+    }
+#endif
+    std::vector<std::vector<uint16_t>> warp_sets;      // closure self-check: sorted slots of warp 0 per chained gate
+    warp_sets.resize(ng);
     for (size_t ci = 0; ci < merged[di].size(); ++ci) {
       const Cluster& cluster = merged[di][ci];
       const GateLayout& gl = layouts[di][ci];
@@ -696,8 +746,16 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       std::vector<unsigned> free_bits;
       if (gd.kind == HQ_GATE_SMALL || gd.kind == HQ_GATE_DR1) {
         for (int u = 0; u < Tu; ++u)
-          if (!is_t[size_t(u + V)]) free_bits.push_back(unsigned(u));
+          if (!is_t[size_t(u + V)] && !((chain_w[ci] >> u) & 1u)) free_bits.push_back(unsigned(u));
         free_bits = lane_order(free_bits);
+        if (chain_w[ci]) {
+          // work-item bits 0..4 = lanes, 5..7 = warp index (the chain's common bits), 8.. = iterations
+          std::vector<unsigned> q(free_bits.begin(), free_bits.begin() + 5);
+          for (int u = 0; u < Tu; ++u)
+            if ((chain_w[ci] >> u) & 1u) q.push_back(unsigned(u));
+          q.insert(q.end(), free_bits.begin() + 5, free_bits.end());
+          free_bits.swap(q);
+        }
       } else if (gd.kind == HQ_GATE_BIG) {
         for (int a = 0; a < Tbits; ++a)
           if (!is_t[size_t(a)]) free_bits.push_back(unsigned(a));
@@ -705,6 +763,20 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       gd.n_free = uint32_t(free_bits.size());
       for (size_t i = 0; i < free_bits.size() && i < 16; ++i) gd.q[i] = uint8_t(free_bits[i]);
       if (gd.kind == HQ_GATE_SMALL || gd.kind == HQ_GATE_DR1) make_lane_tables(gd, Tu, V);
+      if (chain_w[ci]) {
+        // the units warp 0 touches in this gate (all its lanes, all iterations, all units of a work item)
+        const bool low = V == 1 && gd.tpos[0] == 0;
+        const int KK = int(gd.k) - (low ? 1 : 0);
+        const int niter = 1 << (Tu - KK - HQ_THREADS_LOG2);
+        std::vector<uint16_t>& ws = warp_sets[ci];
+        for (int t = 0; t < 32; ++t)
+          for (int it = 0; it < niter; ++it)
+            for (int m = 0; m < (1 << KK); ++m) ws.push_back(uint16_t(gd.tbl_thread[t] ^ gd.tbl_iter[it] ^ gd.tbl_x[m]));
+        std::sort(ws.begin(), ws.end());
+        if (ci > chain_first[ci] && chain_w[ci - 1] == chain_w[ci]) {
+          if (ws == warp_sets[ci - 1]) pi.header.chain_mask |= 1u << (ci - 1);      // gate ci-1 -> ci: warp sync only
+        }
+      }
       if (gd.kind == HQ_GATE_MMA) make_mma_tables(gd, gl.L, V);
       if (gd.kind == HQ_GATE_SMALL && dtype == HQ_DTYPE_C128 && opts.fast_slots != 0 && (gd.k == 2 || gd.k == 3)) {
         make_rowpair_tables(gd, Tu);

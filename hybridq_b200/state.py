@@ -112,6 +112,7 @@ class Plan:
         check(lib.hq_plan_pass_gates(self._h, p, ids, max(1, ng)), "hq_plan_pass_gates")
         return {"tile_bits": out[0], "n_high": out[1], "n_gates": ng, "n_kernel_gates": out[2],
                 "has_perm": out[3], "high_pos": [out[5 + i] for i in range(out[1])],
+                "fast_mask": out[5 + out[1]], "chain_mask": out[6 + out[1]],
                 "gate_ids": [ids[i] for i in range(ng)]}
 
     def run(self, state: "DeviceState", first: int | None = None, last: int | None = None, stream=None):

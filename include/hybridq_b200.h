@@ -173,7 +173,8 @@ int hq_plan_num_kernel_gates(const hq_plan* plan);
  * 8 * 2^k * 2^n (2^k complex multiply-adds per output amplitude) */
 double hq_plan_flops(const hq_plan* plan);
 /* per pass: {tile_bits, n_high, n_kernel_gates, has_perm, n_gate_ids, high_pos[0..n_high)}
- * -> out[0..5+n_high) */
+ * -> out[0..5+n_high); if out_len allows two more: fast_mask (bit s: kernel matrix s runs on a constant-bank FFMA2
+ * slot) and chain_mask (bit s: matrices s and s+1 are separated by a warp-level sync only) */
 int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len);
 /* gate ids (indices into the creation arrays) of a pass, in execution order */
 int hq_plan_pass_gates(const hq_plan* plan, int pass, unsigned int* out, int out_len);
