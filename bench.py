@@ -463,15 +463,25 @@ def main():
         e2e = e2e_through_simulate(hb, runner, gates, n, world, rank, steps=max(1, min(steps, 2)), barrier=barrier,
                                    max_over_ranks=max_over_ranks)
 
+    # release the resident state (collective at N > 1: unmaps the peers' buffers) before anything else allocates
+    del runner
+    hb.clear_caches()
+    torch.cuda.empty_cache()
+
+    def guarded(fn, *a):
+        """The extra configurations must never cost the headline line: a failure is reported in place."""
+        try:
+            return fn(*a)
+        except Exception as e:          # noqa: BLE001
+            torch.cuda.empty_cache()
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
     configs = None
     if not args.no_configs and not args.qubits and SCALING == "strong":
-        del runner
-        hb.clear_caches()
-        torch.cuda.empty_cache()
         if world == 1:
-            configs = {"config3": run_config3(hb, local_rank), "config5": run_config5(hb, local_rank)}
+            configs = {"config3": guarded(run_config3, hb, local_rank), "config5": guarded(run_config5, hb, local_rank)}
         elif world == 8:
-            configs = {"config4": run_config4(hb, dist, rank, local_rank, barrier, max_over_ranks)}
+            configs = {"config4": guarded(run_config4, hb, dist, rank, local_rank, barrier, max_over_ranks)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
