@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "hq_kernels.h"
@@ -365,6 +366,15 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
   }
 }
 
+static bool persistent_grid() {
+  static int persistent = -1;
+  if (persistent < 0) {
+    const char* e = getenv("HQ_PERSISTENT");
+    persistent = (e && atoi(e) > 0) ? 1 : 0;
+  }
+  return persistent == 1;
+}
+
 static int g_tune_nbuf = 0;          // 0 = auto: double-buffer when it costs no resident CTA
 static int g_tune_ctas_per_sm = 0;
 void set_tuning(int nbuf, int ctas_per_sm) {
@@ -430,6 +440,15 @@ static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned ch
   if (per_sm < 1) return int(cudaErrorLaunchOutOfResources);
   if (g_tune_ctas_per_sm > 0 && g_tune_ctas_per_sm < per_sm) per_sm = g_tune_ctas_per_sm;
   unsigned long long grid = (unsigned long long)di.sm_count * (unsigned long long)per_sm;
+  {
+    // One CTA per tile by default: MEASURED on B200 (profiles/r02/bench_o_*.log, n = 30 bench circuit) a persistent
+    // grid of SMs x resident CTAs with a static round-robin of tiles takes 129.0 ms/step, 4 / 32 / 128 times as
+    // many CTAs 125.0 / 123.5 / 119.7 ms and one CTA per tile 117.4 ms: the SMs do not run at one speed (two dies,
+    // near / far L2 slices), and the hardware CTA scheduler refills whichever SM frees up.  HQ_PERSISTENT=1 (or a
+    // grid_override) restores the persistent form; the kernel's tile loop handles either.
+    if (!persistent_grid()) grid = n_tiles;
+    if (grid > (1ull << 30)) grid = 1ull << 30;
+  }
   if (grid_override > 0) grid = (unsigned long long)grid_override;
   if (grid > n_tiles) grid = n_tiles;
   hq_tile_kernel<T, KCLASS, NBUF><<<unsigned(grid), HQ_THREADS, smem, stream>>>(
@@ -446,7 +465,9 @@ static int launch_tile_class(void* state, unsigned n_qubits, const unsigned char
   int rc = variant_occupancy<T, KCLASS, 1>(smem1, di, dev, &occ1);
   if (rc) return rc;
   bool two = false;
-  if (g_tune_nbuf != 1 && smem2 <= size_t(di.max_smem_optin)) {
+  // (with one CTA per tile there is no next tile to prefetch: the double-buffered variant only makes sense on a
+  // persistent grid, or when asked for explicitly)
+  if (g_tune_nbuf != 1 && (persistent_grid() || g_tune_nbuf == 2) && smem2 <= size_t(di.max_smem_optin)) {
     rc = variant_occupancy<T, KCLASS, 2>(smem2, di, dev, &occ2);
     if (rc) return rc;
     two = g_tune_nbuf == 2 ? occ2 >= 1 : occ2 >= occ1;
