@@ -116,6 +116,8 @@ _proto("hq_plan_run", ctypes.c_int, _vp, _vp, _vp)
 _proto("hq_plan_run_range", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp)
 _proto("hq_plan_run_range_xchg", ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_uint,
        _u32p, ctypes.POINTER(_vp), _vp)
+_proto("hq_plan_run_io", ctypes.c_int, _vp, _vp, _vp, _vp, _vp)
+_proto("hq_host_is_pinned", ctypes.c_int, _vp)
 _proto("hq_ipc_get_handle", ctypes.c_int, _vp, _vp)
 _proto("hq_ipc_open", ctypes.c_int, _vp, ctypes.POINTER(_vp))
 _proto("hq_ipc_close", ctypes.c_int, _vp)
@@ -133,7 +135,7 @@ EXPORTED = [
     "hq_unpack_dev", "hq_init_product_dev", "hq_init_random_dev", "hq_norm2_dev", "hq_vdot_dev",
     "hq_scale_dev", "hq_marginal_dev", "hq_project_dev", "hq_marginal_cond_dev", "hq_project_mask_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
     "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_flops", "hq_plan_arith_counts", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
-    "hq_plan_run_range_xchg", "hq_ipc_get_handle", "hq_ipc_open", "hq_ipc_close", "hq_set_ring",
+    "hq_plan_run_range_xchg", "hq_plan_run_io", "hq_host_is_pinned", "hq_ipc_get_handle", "hq_ipc_open", "hq_ipc_close", "hq_set_ring",
     "hq_set_tuning", "hq_launch_count", "hq_launch_count_reset",
 ]
 

@@ -82,10 +82,28 @@ int g_use_direct = 1;   // single k <= 2 gate passes go to the shared-memory-fre
 
 // xchg (may be null): exchange redirect applied to the write-back of the LAST pass of the range
 int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, int first, int last, void* stream,
-                    const hq::HqXchgDesc* xchg = nullptr) {
+                    const hq::HqXchgDesc* xchg = nullptr, const void* io_src = nullptr, void* io_dst = nullptr) {
+  int first_nonempty = -1, last_nonempty = -1;
+  for (int p = first; p < last; ++p) {
+    const HqPassHeader& ph = plan.passes[size_t(p)].header;
+    if (ph.n_gates == 0 && !ph.has_perm) continue;
+    if (first_nonempty < 0) first_nonempty = p;
+    last_nonempty = p;
+  }
   for (int p = first; p < last; ++p) {
     const HqPassHeader& ph = plan.passes[size_t(p)].header;
     const hq::HqXchgDesc* xg = (xchg && xchg->s && p == last - 1) ? xchg : nullptr;
+    hq::HqXchgDesc io;
+    if (io_src || io_dst) {
+      // end-to-end run: the first pass reads the host array, the last pass writes the host array
+      const bool is_first = p == first_nonempty, is_last = p == last_nonempty;
+      if ((is_first && io_src) || (is_last && io_dst)) {
+        memset(&io, 0, sizeof(io));
+        io.src = is_first ? io_src : nullptr;
+        io.dst[0] = (is_last && io_dst) ? io_dst : state;
+        xg = &io;
+      }
+    }
     if (ph.n_gates == 0 && !ph.has_perm && !xg) continue;
     if (g_use_direct && !xg && ph.n_gates == 1 && !ph.has_perm && ph.max_k <= 3 && plan.n_qubits >= ph.max_k + 1) {
       // measured (profiles/): the direct kernel runs a lone 1-/2-/3-qubit gate at copy bandwidth
@@ -626,6 +644,43 @@ int hq_plan_run_range_xchg(hq_plan* plan, void* state, int first, int last, unsi
     pl.device = dev;
   }
   return run_plan_passes(pl, static_cast<const unsigned char*>(pl.d_program), state, first, last, stream, &xg);
+}
+
+int hq_plan_run_io(hq_plan* plan, void* state, const void* host_src, void* host_dst, void* stream) {
+  if (!plan || !state) return fail("null pointer", 1);
+  hq::Plan& pl = plan->plan;
+  bool any = false;
+  for (const hq::PassInfo& pi : pl.passes) any = any || pi.header.n_gates || pi.header.has_perm;
+  if (!any) return fail("plan without passes: copy the state instead", 1);
+  for (const void* p : {host_src, (const void*)host_dst}) {
+    if (!p) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess || (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged)) {
+      cudaGetLastError();
+      return fail("hq_plan_run_io needs pinned (page-locked, mapped) host arrays", 1);
+    }
+  }
+  int dev = 0;
+  HQ_CUDA(cudaGetDevice(&dev));
+  if (pl.d_program && pl.device != dev) {
+    cudaFree(pl.d_program);
+    pl.d_program = nullptr;
+  }
+  if (!pl.d_program) {
+    HQ_CUDA(cudaMalloc(&pl.d_program, pl.program.size()));
+    HQ_CUDA(cudaMemcpy(pl.d_program, pl.program.data(), pl.program.size(), cudaMemcpyHostToDevice));
+    pl.device = dev;
+  }
+  return run_plan_passes(pl, static_cast<const unsigned char*>(pl.d_program), state, 0, int(pl.passes.size()), stream,
+                         nullptr, host_src, host_dst);
+}
+int hq_host_is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return at.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 int hq_ipc_get_handle(void* dptr, void* handle_out_64) {

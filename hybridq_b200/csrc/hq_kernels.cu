@@ -293,12 +293,23 @@ __device__ __forceinline__ void apply_pass_gates(typename Traits<T>::Unit* tile,
   }
 }
 
-template <typename T, int KCLASS, int NBUF>
+struct HqXchg {            // exchange redirect of the drain (all zero = plain in-place pass)
+  uint32_t s;              // number of local index bits swapped with rank bits (0 .. 3)
+  uint32_t mine;           // this rank's digit (value of the rank bits being swapped), deposited at pos[]
+  uint8_t pos[4];          // local AMPLITUDE-bit positions leaving the shard (>= V)
+  uint32_t reserved;
+  void* dst[8];            // destination buffer of digit D (dst[mine] is this rank's own second buffer)
+  const void* src;         // tile kernel only: read the tiles from here instead of `state` (null = state)
+};
+
+// XCHG (NBUF = 1 only): the drain writes to the buffers of HqXchg instead of back in place (see hq_ring_kernel)
+template <typename T, int KCLASS, int NBUF, bool XCHG = false>
 __global__ void __launch_bounds__(HQ_THREADS, ((KCLASS == 0 && Traits<T>::V == 1) ? HQ_K0F_BLOCKS
                                 : ((KCLASS == 1 && Traits<T>::V == 0) ? HQ_K1D_BLOCKS
                                    : ((KCLASS == 1 && Traits<T>::V == 1) ? HQ_K1F_BLOCKS : (KCLASS == 0 ? 3 : 2)))))
 hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char* __restrict__ prog,
-               const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles) {
+               const __grid_constant__ HqPassHeader ph, const unsigned long long n_tiles,
+               const __grid_constant__ HqXchg xg) {
   typedef typename Traits<T>::Unit Unit;
   typedef typename Traits<T>::Cplx Cplx;
   const int V = Traits<T>::V;
@@ -325,6 +336,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     tile_fill<T>(bufs, state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t, ph, swz_t, npt);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
+  const Unit* const fill_src = (XCHG && xg.src) ? reinterpret_cast<const Unit*>(xg.src) : state;
   for (; t < n_tiles; t += gridDim.x) {
     Unit* gptr = state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t;
     Unit* tile = bufs + (size_t(cur) << Tu);
@@ -339,7 +351,7 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       }
     } else {
-      tile_fill<T>(tile, gptr, ph, swz_t, npt);
+      tile_fill<T>(tile, fill_src + (gptr - state), ph, swz_t, npt);
       cp_async_wait_all();
     }
     __syncthreads();
@@ -347,7 +359,33 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
     apply_pass_gates<T, KCLASS, true>(tile, gates, ph, prog, Tbits, Tu, tid, CtaSync());
 
     // drain
-    if (!ph.has_perm) {
+    if (XCHG) {
+      // exchange redirect: unit u of the shard goes to buffer dst[D(u)] at u with the swapped bits set to `mine`
+      uint64_t xmask = 0, xmine = 0;
+      for (uint32_t j = 0; j < xg.s; ++j) {
+        xmask |= uint64_t(1) << (xg.pos[j] - V);
+        xmine |= uint64_t((xg.mine >> j) & 1u) << (xg.pos[j] - V);
+      }
+      const uint64_t ubase = uint64_t(gptr - state);
+      const Cplx* amps = reinterpret_cast<const Cplx*>(tile);
+#pragma unroll 4
+      for (int i = 0; i < npt; ++i) {
+        const uint64_t u = ubase + ph.iter_off[i];
+        Unit v;
+        if (!ph.has_perm) {
+          v = tile[swz_t ^ ph.iter_swz[i]];
+        } else {
+          const uint32_t c = uint32_t(tid) + (uint32_t(i) << HQ_THREADS_LOG2);
+          Cplx o[1 << V];
+#pragma unroll
+          for (uint32_t e = 0; e < (1u << V); ++e) o[e] = amps[amp_slot<T>(perm_src((c << V) | e, ph.perm, Tbits))];
+          v = make_unit(o);
+        }
+        uint32_t D = 0;
+        for (uint32_t j = 0; j < xg.s; ++j) D |= uint32_t((u >> (xg.pos[j] - V)) & 1ull) << j;
+        st_stream(reinterpret_cast<Unit*>(xg.dst[D]) + ((u & ~xmask) | xmine), v);
+      }
+    } else if (!ph.has_perm) {
 #pragma unroll 4
       for (int i = 0; i < npt; ++i) st_stream(gptr + ph.iter_off[i], tile[swz_t ^ ph.iter_swz[i]]);
     } else {
@@ -408,11 +446,11 @@ int device_info(DeviceInfo* out) {
 }
 
 // resident CTAs per SM of one kernel variant at a given dynamic shared-memory size (cached)
-template <typename T, int KCLASS, int NBUF>
+template <typename T, int KCLASS, int NBUF, bool XCHG = false>
 static int variant_occupancy(size_t smem, const DeviceInfo& di, int dev, int* per_sm_out) {
   static bool attr_set[64];
   static int cache[64][HQ_MAX_UNIT_BITS + 2];
-  auto kern = hq_tile_kernel<T, KCLASS, NBUF>;
+  auto kern = hq_tile_kernel<T, KCLASS, NBUF, XCHG>;
   if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
     if (e != cudaSuccess) return int(e);
@@ -433,9 +471,13 @@ static int variant_occupancy(size_t smem, const DeviceInfo& di, int dev, int* pe
   return 0;
 }
 
-template <typename T, int KCLASS, int NBUF>
+template <typename T, int KCLASS, int NBUF, bool XCHG = false>
 static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
-                               cudaStream_t stream, int grid_override, size_t smem, const DeviceInfo& di, int per_sm) {
+                               cudaStream_t stream, int grid_override, size_t smem, const DeviceInfo& di, int per_sm,
+                               const HqXchg* xgp = nullptr) {
+  HqXchg xg;
+  if (xgp) xg = *xgp;
+  else memset(&xg, 0, sizeof(xg));
   const unsigned long long n_tiles = 1ull << (n_qubits - ph.tile_bits);
   if (per_sm < 1) return int(cudaErrorLaunchOutOfResources);
   if (g_tune_ctas_per_sm > 0 && g_tune_ctas_per_sm < per_sm) per_sm = g_tune_ctas_per_sm;
@@ -451,8 +493,8 @@ static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned ch
   }
   if (grid_override > 0) grid = (unsigned long long)grid_override;
   if (grid > n_tiles) grid = n_tiles;
-  hq_tile_kernel<T, KCLASS, NBUF><<<unsigned(grid), HQ_THREADS, smem, stream>>>(
-      reinterpret_cast<typename Traits<T>::Unit*>(state), prog, ph, n_tiles);
+  hq_tile_kernel<T, KCLASS, NBUF, XCHG><<<unsigned(grid), HQ_THREADS, smem, stream>>>(
+      reinterpret_cast<typename Traits<T>::Unit*>(state), prog, ph, n_tiles, xg);
   return int(cudaGetLastError());
 }
 
@@ -474,6 +516,29 @@ static int launch_tile_class(void* state, unsigned n_qubits, const unsigned char
   }
   if (two) return launch_tile_variant<T, KCLASS, 2>(state, n_qubits, prog, ph, stream, grid_override, smem2, di, occ2);
   return launch_tile_variant<T, KCLASS, 1>(state, n_qubits, prog, ph, stream, grid_override, smem1, di, occ1);
+}
+
+// exchange-redirect pass on the tile kernel (single-buffered, one CTA per tile)
+template <typename T, int KCLASS>
+static int launch_tile_xchg_class(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                                  const HqXchg& xg, cudaStream_t stream, int grid_override, const DeviceInfo& di, int dev) {
+  const int dtype = Traits<T>::V == 1 ? HQ_DTYPE_C64 : HQ_DTYPE_C128;
+  const size_t smem1 = tile_pass_smem_bytes(ph, dtype, 1);
+  int occ = 0;
+  const int rc = variant_occupancy<T, KCLASS, 1, true>(smem1, di, dev, &occ);
+  if (rc) return rc;
+  return launch_tile_variant<T, KCLASS, 1, true>(state, n_qubits, prog, ph, stream, grid_override, smem1, di, occ, &xg);
+}
+template <typename T>
+static int launch_tile_xchg_t(void* state, unsigned n_qubits, const unsigned char* prog, const HqPassHeader& ph,
+                              const HqXchg& xg, cudaStream_t stream, int grid_override, const DeviceInfo& di, int dev) {
+  const int kclass = ph.max_k <= 2 ? 0 : (ph.max_k <= 3 ? 1 : (ph.max_k <= 4 ? 2 : 3));
+  switch (kclass) {
+    case 0: return launch_tile_xchg_class<T, 0>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+    case 1: return launch_tile_xchg_class<T, 1>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+    case 2: return launch_tile_xchg_class<T, 2>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+    default: return launch_tile_xchg_class<T, 3>(state, n_qubits, prog, ph, xg, stream, grid_override, di, dev);
+  }
 }
 
 template <typename T>
@@ -556,13 +621,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-struct HqXchg {            // exchange redirect of the drain (all zero = plain in-place pass)
-  uint32_t s;              // number of local index bits swapped with rank bits (0 .. 3)
-  uint32_t mine;           // this rank's digit (value of the rank bits being swapped), deposited at pos[]
-  uint8_t pos[4];          // local AMPLITUDE-bit positions leaving the shard (>= V)
-  uint32_t reserved;
-  void* dst[8];            // destination buffer of digit D (dst[mine] is this rank's own second buffer)
-};
 
 template <typename T, int KCLASS, bool XCHG>
 __global__ void __launch_bounds__(HQ_RING_THREADS, 1)
@@ -731,8 +789,9 @@ int launch_pass(int dtype, void* state, unsigned n_qubits, const unsigned char* 
   const bool can_ring = ring_eligible(ph, dtype, n_qubits, di);
   HqXchg xg;
   memset(&xg, 0, sizeof(xg));
-  if (xchg && xchg->s) {
+  if (xchg && (xchg->s || xchg->src || xchg->dst[0])) {
     if (!can_ring || xchg->s > 3) return int(cudaErrorInvalidValue);
+    xg.src = xchg->src;
     const unsigned V = dtype == HQ_DTYPE_C64 ? 1u : 0u;
     xg.s = xchg->s;
     xg.mine = xchg->mine;
@@ -741,9 +800,18 @@ int launch_pass(int dtype, void* state, unsigned n_qubits, const unsigned char* 
       xg.pos[j] = (uint8_t)xchg->pos[j];
     }
     for (unsigned d = 0; d < (1u << xchg->s); ++d) {
-      if (!xchg->dst[d]) return int(cudaErrorInvalidValue);
-      xg.dst[d] = xchg->dst[d];
+      if (!xchg->dst[d] && xchg->s) return int(cudaErrorInvalidValue);
+      xg.dst[d] = xchg->dst[d] ? xchg->dst[d] : state;      // s = 0: in place unless a destination is given
     }
+    // which kernel carries the redirect: the tile kernel (three CTAs per SM, one per tile) unless HQ_XCHG_RING=1
+    static int xchg_ring = -1;
+    if (xchg_ring < 0) {
+      const char* e = getenv("HQ_XCHG_RING");
+      xchg_ring = (e && atoi(e) > 0) ? 1 : 0;
+    }
+    if ((!xchg_ring || xg.src) && tile_pass_smem_bytes(ph, dtype, 1) <= size_t(di.max_smem_optin))
+      return dtype == HQ_DTYPE_C64 ? launch_tile_xchg_t<float>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev)
+                                   : launch_tile_xchg_t<double>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev);
     return dtype == HQ_DTYPE_C64 ? launch_ring_t<float, true>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev)
                                  : launch_ring_t<double, true>(state, n_qubits, prog, ph, xg, s, grid_override, di, dev);
   }

@@ -34,6 +34,9 @@ struct HqXchgDesc {
   unsigned mine;
   unsigned pos[4];
   void* dst[8];
+  // optional: the pass reads its tiles from `src` instead of the state buffer (same layout; e.g. a pinned host
+  // array for the first pass of an end-to-end run); with s = 0, dst[0] is where the whole result goes
+  const void* src;
 };
 // One pass over the state: the pipelined ring kernel (hq_ring_kernel) for large states, hq_tile_kernel otherwise.
 // xchg may be null.  ring mode: -1 auto, 0 never, 1 whenever the tile allows it (tests).

@@ -127,6 +127,21 @@ class Plan:
                                             _stream_handle(stream, state.device)), "hq_plan_run_range")
 
 
+    def run_io(self, state: "DeviceState", host_src: np.ndarray | None, host_dst: np.ndarray | None, stream=None):
+        """All passes with the upload and / or download folded in (hq_plan_run_io): the first pass reads its tiles
+        from the PINNED host array `host_src`, the last pass writes the result to the PINNED host array `host_dst`.
+        Asynchronous; call state.sync() before reading `host_dst`."""
+        if state.n_qubits != self.n_qubits or state.dtype != self.dtype:
+            raise ValueError("plan and state disagree on size or precision")
+        for a in (host_src, host_dst):
+            if a is not None and (a.size != state.n_amps or a.dtype != state.complex_type or not a.flags.c_contiguous):
+                raise ValueError("host arrays must be contiguous, of the state's size and precision")
+        with _on(state.device):
+            check(lib.hq_plan_run_io(self._h, state.ptr,
+                                     ctypes.c_void_p(host_src.ctypes.data) if host_src is not None else None,
+                                     ctypes.c_void_p(host_dst.ctypes.data) if host_dst is not None else None,
+                                     _stream_handle(stream, state.device)), "hq_plan_run_io")
+
     def run_xchg(self, state: "DeviceState", gbit_digit: int, lpos: Sequence[int], dst_ptrs: Sequence[int], stream=None):
         """All passes, the last one with its write-back redirected (hq_plan_run_range_xchg): the amplitudes whose
         local index bits `lpos` spell D go to the buffer `dst_ptrs[D]` at the same index with those bits replaced

@@ -198,6 +198,12 @@ int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len);
  * hq_ipc_*: cudaIpc plumbing for the peer buffers (handle = 64 bytes, exchanged by the host code). */
 int hq_plan_run_range_xchg(hq_plan* plan, void* state, int first, int last, unsigned int s, unsigned int mine,
                            const unsigned int* pos, void* const* dst, void* stream);
+/* End-to-end run over PINNED host arrays (same interleaved layout as the device state): the first pass reads its
+ * tiles straight from host_src over PCIe and the last pass writes its result straight to host_dst, so the upload and
+ * the download overlap the arithmetic of those passes instead of being separate copies (either may be NULL; `state`
+ * is the device working buffer and holds the result too unless host_dst is given).  Asynchronous on the stream. */
+int hq_plan_run_io(hq_plan* plan, void* state, const void* host_src, void* host_dst, void* stream);
+int hq_host_is_pinned(const void* ptr);
 int hq_ipc_get_handle(void* dptr, void* handle_out_64);
 int hq_ipc_open(const void* handle_64, void** dptr);
 int hq_ipc_close(void* dptr);

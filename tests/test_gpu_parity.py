@@ -445,3 +445,31 @@ def test_checkpoint_round_trip_and_sampling(hb, tmp_path):
     top = np.bincount(draws >> (n - 4), minlength=16) / 50000
     want = back.marginal(list(range(n - 4, n))).sum(axis=1)
     assert np.abs(top - want).max() < 0.02
+
+
+def test_simulate_with_pinned_host_arrays_folds_the_transfers(hb, oracle, c_oracle):
+    """hq_plan_run_io: with pinned `initial_state` / `out` the first pass reads the host array and the last pass
+    writes the host array; same result as the copy-in / copy-out path and as the oracle, for one pass and many."""
+    import torch
+    from hybridq_b200.circuits import matching_circuit, to_positions, random_state
+    for n, depth, ctype in ((17, 6, "complex64"), (12, 2, "complex128"), (18, 3, "complex64")):
+        gates = matching_circuit(n, depth=depth, seed=n)     # n = 12 complex128 is one tile: a single pass carries
+                                                             # the upload and the download
+        lowered, _ = to_positions(gates, qubits=list(range(n)))
+        psi0 = random_state(n, ctype, seed=4)
+        ref = oracle.evolve_oracle(psi0, [(U.astype(ctype), p) for U, p in lowered], c_oracle)
+        tdt = torch.complex64 if ctype == "complex64" else torch.complex128
+        h_in = torch.empty(2 ** n, dtype=tdt, pin_memory=True)
+        h_out = torch.empty(2 ** n, dtype=tdt, pin_memory=True)
+        h_in.numpy()[:] = psi0
+        h_out.zero_()
+        psi, info = hb.simulate(gates, initial_state=h_in.numpy().reshape((2,) * n), complex_type=ctype,
+                                out=h_out.numpy(), return_info=True)
+        assert info["transfers folded into passes"] == {"upload": True, "download": True}
+        assert np.abs(h_out.numpy() - ref).max() <= TOL[ctype]
+        assert np.shares_memory(psi, h_out.numpy())
+        assert np.array_equal(h_in.numpy(), psi0)            # the input is left alone
+        # pageable arrays take the ordinary path and give the same numbers
+        plain, info2 = hb.simulate(gates, initial_state=psi0.reshape((2,) * n), complex_type=ctype, return_info=True)
+        assert info2["transfers folded into passes"] == {"upload": False, "download": False}
+        assert np.abs(plain.reshape(-1) - h_out.numpy()).max() <= TOL[ctype]
