@@ -29,6 +29,9 @@
 #ifndef HQ_MMA_BREG_KS
 #define HQ_MMA_BREG_KS 4  // gates with 2^k / 4 <= this keep their B fragments in registers for the whole gate
 #endif
+#ifndef HQ_TILE_QUEUE
+#define HQ_TILE_QUEUE 0   // 1: persistent grid + global tile counter instead of one CTA per tile (experiment)
+#endif
 #ifndef HQ_K1F_BLOCKS
 #define HQ_K1F_BLOCKS 2   // resident CTAs per SM of the k <= 3 complex64 tile kernel (128 registers: the k = 3 FFMA2 slots keep 16 accumulator pairs)
 #endif
@@ -300,6 +303,7 @@ struct HqXchg {            // exchange redirect of the drain (all zero = plain i
   uint32_t reserved;
   void* dst[8];            // destination buffer of digit D (dst[mine] is this rank's own second buffer)
   const void* src;         // tile kernel only: read the tiles from here instead of `state` (null = state)
+  unsigned long long* queue;   // tile kernel, HQ_TILE_QUEUE builds: tile counter of a persistent grid (null = static)
 };
 
 // XCHG (NBUF = 1 only): the drain writes to the buffers of HqXchg instead of back in place (see hq_ring_kernel)
@@ -331,13 +335,29 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
   const uint32_t swz_t = swz(uint32_t(tid));
 
   unsigned long long t = blockIdx.x;
+#if HQ_TILE_QUEUE
+  // persistent grid fed from a global tile counter: the next tile index is fetched while the current tile is being
+  // processed (thread 0, right after the fill barrier) and read after the barrier that ends the tile
+  // (the slot lives behind the tile in the dynamic shared memory: tile_pass_smem_bytes adds 16 bytes)
+  volatile unsigned long long& s_next = *reinterpret_cast<volatile unsigned long long*>(smem + (size_t(16 * NBUF) << Tu));
+  unsigned long long* const queue = NBUF == 1 ? xg.queue : nullptr;
+  if (queue) {
+    if (tid == 0) s_next = atomicAdd(queue, 1ull);
+    __syncthreads();
+    t = s_next;
+  }
+#endif
   int cur = 0;
   if (NBUF == 2 && t < n_tiles) {
     tile_fill<T>(bufs, state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t, ph, swz_t, npt);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
   const Unit* const fill_src = (XCHG && xg.src) ? reinterpret_cast<const Unit*>(xg.src) : state;
+#if HQ_TILE_QUEUE
+  for (; t < n_tiles; t = queue ? s_next : t + gridDim.x) {
+#else
   for (; t < n_tiles; t += gridDim.x) {
+#endif
     Unit* gptr = state + (tile_base(t, Tbits, h, ph.high_pos) >> V) + off_t;
     Unit* tile = bufs + (size_t(cur) << Tu);
     if (NBUF == 2) {
@@ -355,6 +375,9 @@ hq_tile_kernel(typename Traits<T>::Unit* __restrict__ state, const unsigned char
       cp_async_wait_all();
     }
     __syncthreads();
+#if HQ_TILE_QUEUE
+    if (queue && tid == 0) s_next = atomicAdd(queue, 1ull);     // everybody has read the previous value by now
+#endif
 
     apply_pass_gates<T, KCLASS, true>(tile, gates, ph, prog, Tbits, Tu, tid, CtaSync());
 
@@ -423,7 +446,7 @@ void set_tuning(int nbuf, int ctas_per_sm) {
 size_t tile_pass_smem_bytes(const HqPassHeader& ph, int dtype, int nbuf) {
   const int V = dtype == HQ_DTYPE_C64 ? 1 : 0;
   const int Tu = int(ph.tile_bits) - V;
-  return size_t(16 * nbuf) << Tu;
+  return (size_t(16 * nbuf) << Tu) + (HQ_TILE_QUEUE ? 16 : 0);
 }
 
 static DeviceInfo g_info[64];
@@ -460,7 +483,7 @@ static int variant_occupancy(size_t smem, const DeviceInfo& di, int dev, int* pe
     attr_set[dev] = true;
   }
   int slot = 0;
-  while ((size_t(16 * NBUF) << slot) < smem && slot < HQ_MAX_UNIT_BITS + 1) ++slot;
+  while ((size_t(16 * NBUF) << slot) + (HQ_TILE_QUEUE ? 16 : 0) < smem && slot < HQ_MAX_UNIT_BITS + 1) ++slot;
   if (cache[dev][slot] < 0) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HQ_THREADS, smem);
@@ -478,6 +501,23 @@ static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned ch
   HqXchg xg;
   if (xgp) xg = *xgp;
   else memset(&xg, 0, sizeof(xg));
+#if HQ_TILE_QUEUE
+  bool use_queue = false;
+  if (NBUF == 1 && grid_override <= 0) {
+    // a ring of 64 tile counters per device; each launch zeroes the one it uses in stream order
+    static unsigned long long* q[64];
+    static unsigned qi[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!q[dev] && cudaMalloc(reinterpret_cast<void**>(&q[dev]), 64 * sizeof(unsigned long long)) != cudaSuccess) q[dev] = nullptr;
+    if (q[dev]) {
+      xg.queue = q[dev] + (qi[dev]++ & 63u);
+      if (cudaMemsetAsync(xg.queue, 0, sizeof(unsigned long long), stream) == cudaSuccess) use_queue = true;
+      else xg.queue = nullptr;
+    }
+  }
+#endif
   const unsigned long long n_tiles = 1ull << (n_qubits - ph.tile_bits);
   if (per_sm < 1) return int(cudaErrorLaunchOutOfResources);
   if (g_tune_ctas_per_sm > 0 && g_tune_ctas_per_sm < per_sm) per_sm = g_tune_ctas_per_sm;
@@ -488,7 +528,11 @@ static int launch_tile_variant(void* state, unsigned n_qubits, const unsigned ch
     // many CTAs 125.0 / 123.5 / 119.7 ms and one CTA per tile 117.4 ms: the SMs do not run at one speed (two dies,
     // near / far L2 slices), and the hardware CTA scheduler refills whichever SM frees up.  HQ_PERSISTENT=1 (or a
     // grid_override) restores the persistent form; the kernel's tile loop handles either.
+#if HQ_TILE_QUEUE
+    if (!persistent_grid() && !use_queue) grid = n_tiles;
+#else
     if (!persistent_grid()) grid = n_tiles;
+#endif
     if (grid > (1ull << 30)) grid = 1ull << 30;
   }
   if (grid_override > 0) grid = (unsigned long long)grid_override;
