@@ -105,10 +105,13 @@ int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, in
       }
     }
     if (ph.n_gates == 0 && !ph.has_perm && !xg) continue;
-    if (g_use_direct && !xg && ph.n_gates == 1 && !ph.has_perm && ph.max_k <= 3 && plan.n_qubits >= ph.max_k + 1) {
+    HqGateDesc gd;
+    if (ph.n_gates == 1) memcpy(&gd, plan.program.data() + ph.gates_off, sizeof(gd));
+    // (the gate's own k and kind decide, not the header's kernel class: a lone scalar + rank-one k = 4 gate carries
+    // max_k = 3 -- found by tools/sanitize_target.py in round 2)
+    if (g_use_direct && !xg && ph.n_gates == 1 && !ph.has_perm && gd.kind == HQ_GATE_SMALL && gd.k <= 3 &&
+        plan.n_qubits >= gd.k + 1) {
       // measured (profiles/): the direct kernel runs a lone 1-/2-/3-qubit gate at copy bandwidth
-      HqGateDesc gd;
-      memcpy(&gd, plan.program.data() + ph.gates_off, sizeof(gd));
       const unsigned L = ph.tile_bits - ph.n_high;
       unsigned pos[4];
       for (unsigned i = 0; i < gd.k; ++i) pos[i] = gd.tpos[i] < L ? gd.tpos[i] : ph.high_pos[gd.tpos[i] - L];

@@ -473,3 +473,21 @@ def test_simulate_with_pinned_host_arrays_folds_the_transfers(hb, oracle, c_orac
         plain, info2 = hb.simulate(gates, initial_state=psi0.reshape((2,) * n), complex_type=ctype, return_info=True)
         assert info2["transfers folded into passes"] == {"upload": False, "download": False}
         assert np.abs(plain.reshape(-1) - h_out.numpy()).max() <= TOL[ctype]
+
+
+def test_lone_scalar_plus_rank_one_gate(hb, oracle, c_oracle):
+    """A pass holding ONE scalar + rank-one k = 4 gate (fuse = 0, or simply a one-gate circuit) must take the tile
+    kernel, not the k <= 3 direct kernel (regression: the header's kernel class is 3 for such a gate)."""
+    rng = np.random.default_rng(12)
+    n = 14
+    u = rng.standard_normal(16) + 1j * rng.standard_normal(16)
+    U = 0.95 * np.eye(16) + 0.01 * np.outer(u, u.conj())
+    for ctype in ("complex64", "complex128"):
+        psi = _rand_state(rng, n, ctype)
+        ref = oracle.evolve_oracle(psi, [(U.astype(ctype), [2, 5, 8, 11])], c_oracle)
+        for opts in (None, hb.PlanOptions(fuse=0)):
+            st = hb.DeviceState(n, ctype).upload(psi)
+            plan = hb.Plan([(U, [2, 5, 8, 11])], n, ctype, opts)
+            assert plan.arithmetic() == {"k4": {"scalar_plus_rank_one": 1}}
+            plan.run(st)
+            assert np.abs(st.download() - ref).max() <= TOL[ctype]
