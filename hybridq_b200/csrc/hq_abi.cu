@@ -78,6 +78,8 @@ void fill_gate(hq::GateIn& g, const T* U, const unsigned* pos, unsigned k) {
   for (size_t i = 0; i < e; ++i) g.U[i] = std::complex<double>(double(U[2 * i]), double(U[2 * i + 1]));
 }
 
+int g_use_umma = 1;     // complex64 passes made of one dense k = 4 / 5 matrix go to the tcgen05 kernel (hq_umma.cuh)
+std::atomic<uint64_t> g_umma_launches{0};
 int g_use_direct = 1;   // single k <= 2 gate passes go to the shared-memory-free kernel
 
 // xchg (may be null): exchange redirect applied to the write-back of the LAST pass of the range
@@ -119,6 +121,17 @@ int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, in
                                             gd.k, stream);
       if (rc) return cuda_fail("direct gate launch", rc);
       ++g_launches;
+      continue;
+    }
+    if (g_use_umma && !xg && plan.passes[size_t(p)].umma_off && ph.n_gates == 1 && d_prog) {
+      // measured (profiles/r02): 1.9x (k = 4) / 2.3x (k = 5) the bandwidth of the mma.sync tile-kernel path
+      const unsigned L = ph.tile_bits - ph.n_high;
+      unsigned pos[8];
+      for (unsigned i = 0; i < gd.k; ++i) pos[i] = gd.tpos[i] < L ? gd.tpos[i] : ph.high_pos[gd.tpos[i] - L];
+      const int rc = hq::launch_umma(state, plan.n_qubits, pos, gd.k, d_prog + plan.passes[size_t(p)].umma_off, stream);
+      if (rc) return cuda_fail("tcgen05 gate launch", rc);
+      ++g_launches;
+      ++g_umma_launches;
       continue;
     }
     const int rc = hq::launch_pass(plan.dtype, state, plan.n_qubits, d_prog, ph, xg, stream, 0);
@@ -720,6 +733,19 @@ int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct) {
 int hq_set_ring(int mode) {
   hq::set_ring(mode);
   return 0;
+}
+
+int hq_set_umma(int mode) {
+  const int old = g_use_umma;
+  if (mode >= 0) g_use_umma = mode ? 1 : 0;
+  return old;
+}
+uint64_t hq_umma_launch_count(void) { return g_umma_launches.load(); }
+int hq_plan_umma_passes(const hq_plan* plan) {
+  if (!plan) return -1;
+  int cnt = 0;
+  for (const hq::PassInfo& pi : plan->plan.passes) cnt += pi.umma_off ? 1 : 0;
+  return cnt;
 }
 
 uint64_t hq_launch_count(void) { return g_launches.load(); }

@@ -46,6 +46,10 @@ void set_ring(int mode);
 
 // Direct (no shared memory) single-gate kernel for k <= 3 with every target at or above
 // amplitude bit `V` (see hq_kernels.cu); U is read from kernel parameters.
+// tcgen05 / TMEM kernel for ONE dense complex64 gate, k = 4 or 5, n_qubits >= k + 7 (hq_umma.cuh).  pos ascending;
+// d_operands = device pointer to the B_hi, B_lo blocks written by umma_pack_matrix (hq_plan.h).  Returns a cudaError.
+int launch_umma(void* state, unsigned n_qubits, const unsigned* pos, unsigned k, const void* d_operands, void* stream);
+
 int launch_direct_gate(int dtype, void* state, unsigned n_qubits, const void* U_host,
                        const unsigned* pos_sorted, unsigned k, void* stream);
 

@@ -809,7 +809,46 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     }
     plan.passes.push_back(std::move(pi));
   }
+  // ---- tcgen05 operand blocks for passes made of one dense complex64 k = 4 / 5 matrix (hq_umma.cuh) ----
+  if (dtype == HQ_DTYPE_C64) {
+    for (size_t di = 0; di < drafts.size(); ++di) {
+      if (merged[di].size() != 1 || !layouts[di][0].mma || layouts[di][0].dr1) continue;
+      const Canon& c = merged[di][0].gate;
+      if (c.k < UMMA_MIN_K || c.k > UMMA_MAX_K || n < c.k + UMMA_ROW_BITS || plan.passes[di].header.has_perm) continue;
+      const size_t R = size_t(2) << c.k, floats = R * R;
+      const size_t at = (plan.program.size() + 15) & ~size_t(15);
+      if (at + 2 * floats * 4 + 16 > 0xffffffffull) break;
+      plan.program.resize(at + 2 * floats * 4 + 16, 0);
+      float* hi = reinterpret_cast<float*>(plan.program.data() + at);
+      umma_pack_matrix(c.U.data(), c.k, hi, hi + floats);
+      plan.passes[di].umma_off = uint32_t(at);
+    }
+  }
   return 0;
+}
+
+namespace {
+float tf32_round_nearest(float x) {      // cvt.rna.tf32.f32: nearest, ties away from zero
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  b = (b + 0x1000u) & 0xffffe000u;
+  memcpy(&x, &b, 4);
+  return x;
+}
+}  // namespace
+
+void umma_pack_matrix(const std::complex<double>* U, unsigned k, float* hi, float* lo) {
+  const size_t dim = size_t(1) << k, R = 2 * dim;
+  for (size_t nn = 0; nn < R; ++nn)
+    for (size_t kk = 0; kk < R; ++kk) {
+      const size_t i = nn >> 1, ri = nn & 1, j = kk >> 1, rj = kk & 1;
+      const float re = float(U[i * dim + j].real()), im = float(U[i * dim + j].imag());
+      const float v = ri == rj ? re : (ri == 0 ? -im : im);      // (re, im) of the output from (re, im) of the input
+      const float h = tf32_round_nearest(v);
+      const size_t at = ((kk >> 2) * R + nn) * 4 + (kk & 3);
+      hi[at] = h;
+      lo[at] = tf32_round_nearest(v - h);
+    }
 }
 
 void make_identity_pass(int dtype, unsigned n, HqPassHeader& ph) {

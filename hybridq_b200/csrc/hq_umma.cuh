@@ -1,0 +1,400 @@
+// hq_umma.cuh -- one dense k = 3 .. 5 gate on a complex64 state with the 5th-generation tensor cores:
+// `tcgen05.mma kind::tf32` issued by one thread per CTA, accumulators in TMEM, `tcgen05.ld` epilogue.
+//
+// This is the "genuine dense contraction" case of the north star (replaces the runtime-k loop of
+// /root/reference/include/U.h:123-202): per group of 2^k amplitudes the gate is the real product (k = 5 shown)
+//     D[1 x 64] = A[1 x 64] * Bs^T,   A = the group's reals (re, im interleaved), Bs = real form of U,
+// and a CTA multiplies 128 groups at a time: M = 128, N = K = 64.  Accuracy: 3xTF32 -- hi * hi + lo * hi + hi * lo with
+// hi = the operand rounded to TF32 (nearest) and lo = the rounded remainder, all summed in the fp32 TMEM accumulator.
+//
+// Operand layout (K-major, no swizzle, validated bit-exact by tools/microbench_tcgen05.cu): 16-byte units,
+//     A unit (row r, K-chunk c)  at shared slot  c * 128 + r      (LBO = 128 units, SBO = 8 units)
+//     B unit (row n, K-chunk c)  at shared slot  c * N   + n      (LBO = N   units, SBO = 8 units)
+// An A unit holds 4 consecutive reals = the two amplitudes 2c, 2c + 1 of the group, i.e. the pair that differs in
+// the gate's LOWEST target bit: thread r gathers them from global memory with 8-byte loads (for a fixed amplitude
+// number the 32 lanes of a warp read consecutive groups: contiguous when bit 0 is not a target), splits hi / lo in
+// registers and stores both copies with conflict-free 16-byte shared stores.  The epilogue reads row r of D back
+// from TMEM lane r and scatters the 32 output amplitudes with 8-byte stores.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+// hi * hi accumulators per tile (see the kernel); 3 is what fits next to the correction accumulator for k = 5
+#ifndef HQ_UMMA_NACC
+#define HQ_UMMA_NACC 3
+#endif
+// timing experiments only (wrong results): 1 = every MMA into accumulator 0, the epilogue unchanged
+#ifndef HQ_UMMA_DEBUG_ONE_CHAIN
+#define HQ_UMMA_DEBUG_ONE_CHAIN 0
+#endif
+
+namespace hq {
+
+struct UmmaPos {
+  unsigned char tpos[8];     // ascending amplitude-bit positions of matrix bits 0 .. k-1
+};
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// shared-memory matrix descriptor: start address, LBO, SBO in 16-byte units; version 1 (Blackwell); no swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3fffu);
+  d |= uint64_t(lbo_units & 0x3fffu) << 16;
+  d |= uint64_t(sbo_units & 0x3fffu) << 32;
+  d |= uint64_t(1) << 46;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, dense, M = 128, N
+__host__ __device__ inline uint32_t instr_desc(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;             // c_format = F32
+  d |= 2u << 7;             // a_format = TF32
+  d |= 2u << 10;            // b_format = TF32
+  d |= (n >> 3) << 17;      // n_dim
+  d |= (128u >> 4) << 24;   // m_dim
+  return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u));
+}
+// spin on an mbarrier phase; traps instead of hanging the GPU if the protocol is broken
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spins > (1u << 26)) __trap();
+  }
+}
+// 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
+// fp32 -> TF32, round to nearest (ties away): unlike truncation it leaves no bias for the norm to drift on
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// 16 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+template <int CB>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[32]) {
+  if (CB == 32) tmem_ld32(taddr, v);
+  else tmem_ld16(taddr, v);
+}
+
+}  // namespace umma
+
+// TMEM columns of one CTA: up to three hi * hi accumulators and one for the corrections, R columns each (power of two)
+template <int KQ>
+__host__ __device__ constexpr int umma_tmem_cols() {
+  return KQ == 5 ? 256 : (KQ == 4 ? 128 : 64);
+}
+
+// How a warp's lanes are spread over a tile's 16-byte units while it is loaded and stored:
+//   rows   (MODEB = false): lane = 5 low row bits; thread r owns row r, iteration i handles K-chunk i.  Best when the
+//                           low amplitude bits are not targets (consecutive groups are contiguous in memory).
+//   mixed  (MODEB = true):  lane = 3 low row bits x 2 low K-chunk bits, for gates whose targets include low bits
+//                           (then consecutive K-chunks are the contiguous ones).  The epilogue is staged through the
+//                           (free) A_hi buffer so that the stores use the same mapping.
+// Both keep every 16-byte shared store / load conflict free (8 consecutive lanes = 8 consecutive rows of one chunk).
+// PAIR16: the lowest target is amplitude bit 0, so a unit is 16 contiguous bytes in memory (one 128-bit access).
+//
+// state: 2^n interleaved complex64 amplitudes; n_tiles = 2^(n - KQ - 7) tiles of 128 groups
+template <int KQ, bool MODEB, bool PAIR16>
+__global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ state, const unsigned long long n_tiles,
+                                                           const UmmaPos p, const float4* __restrict__ Bhi,
+                                                           const float4* __restrict__ Blo) {
+  constexpr int DIM = 1 << KQ;       // amplitudes per group
+  constexpr int R = 2 * DIM;         // reals per group = N = K
+  constexpr int CH = R / 4;          // 16-byte K-chunks per row
+  static_assert(KQ >= 3 && KQ <= 5, "tile and TMEM budget are sized for k = 3 .. 5");
+  // The tensor core adds into its fp32 accumulator with truncation (round toward zero); chaining all 3 * R / 8 MMAs
+  // through one accumulator shrinks every amplitude by ~7e-7 per gate (measured: norm - 1 = -2.0e-4 after 300 k = 5
+  // gates).  So the big hi * hi products go to NACC separate accumulators (chains of at most 3 K-steps, each starting
+  // from zero), the small lo * hi and hi * lo corrections to one more, and the epilogue adds them with
+  // round-to-nearest FADDs (the scheme of hq_mma.cuh, within the 512-column TMEM budget of two CTAs per SM).
+  constexpr int KSTEPS = R / 8;
+  constexpr int NACC = KSTEPS < HQ_UMMA_NACC ? KSTEPS : HQ_UMMA_NACC;
+  constexpr int COLS = umma_tmem_cols<KQ>();
+  static_assert((NACC + 1) * R <= COLS, "TMEM columns");
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* const sAhi = reinterpret_cast<float4*>(smem);
+  float4* const sAlo = sAhi + CH * 128;
+  float4* const sBhi = sAlo + CH * 128;
+  float4* const sBlo = sBhi + CH * R;
+  unsigned long long* const dep = reinterpret_cast<unsigned long long*>(sBlo + CH * R);   // dep[j]: offset of amplitude j
+  unsigned long long* const rowoff = dep + DIM;                                            // rowoff[r]: offset of row r
+  unsigned long long* const bar = rowoff + 128;
+  uint32_t* const tmem_holder = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // group index -> amplitude index with zeros at the target bits (a bit permutation: OR-separable)
+  auto spread = [&](unsigned long long g) {
+#pragma unroll
+    for (int b = 0; b < KQ; ++b) {
+      const unsigned long long low = (1ull << p.tpos[b]) - 1ull;
+      g = ((g & ~low) << 1) | (g & low);
+    }
+    return g;
+  };
+  for (int i = tid; i < CH * R; i += 128) {
+    sBhi[i] = Bhi[i];
+    sBlo[i] = Blo[i];
+  }
+  if (tid < DIM) {
+    unsigned long long d = 0;
+    for (int b = 0; b < KQ; ++b) d |= (unsigned long long)((tid >> b) & 1) << p.tpos[b];
+    dep[tid] = d;
+  }
+  rowoff[tid] = spread((unsigned long long)tid);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(umma::smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(tmem_holder)),
+                 "r"(uint32_t(COLS)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t idesc = umma::instr_desc(R);
+  const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo), b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
+  const unsigned long long pair_bit = 1ull << p.tpos[0];
+
+  // unit handled by this thread in iteration i: shared slot and amplitude offset inside the tile
+  auto unit_slot = [&](int i) {
+    if (!MODEB) return i * 128 + tid;
+    const int q = warp * CH + i;
+    return (4 * (q >> 4) + (lane >> 3)) * 128 + 8 * (q & 15) + (lane & 7);
+  };
+  auto unit_off = [&](int i) {
+    const int slot = unit_slot(i);
+    return rowoff[slot & 127] | dep[2 * (slot >> 7)];
+  };
+  // one tile's units in registers: every load of a tile is in flight at once, and the loads of the NEXT tile are
+  // issued right after this tile's MMAs so that they overlap the tensor-core work and the epilogue
+  float4 x[CH];
+  auto load_tile = [&](unsigned long long tbase) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const unsigned long long a = tbase | unit_off(i);
+      if (PAIR16) {
+        x[i] = *reinterpret_cast<const float4*>(&state[a]);
+      } else {
+        const float2 x0 = state[a], x1 = state[a | pair_bit];
+        x[i] = make_float4(x0.x, x0.y, x1.x, x1.y);
+      }
+    }
+  };
+  auto store_unit = [&](unsigned long long a, const float4 v) {
+    if (PAIR16) {
+      *reinterpret_cast<float4*>(&state[a]) = v;
+    } else {
+      state[a] = make_float2(v.x, v.y);
+      state[a | pair_bit] = make_float2(v.z, v.w);
+    }
+  };
+  unsigned long long tile = blockIdx.x;
+  unsigned long long tbase = tile < n_tiles ? spread(tile * 128ull) : 0ull;
+  if (tile < n_tiles) load_tile(tbase);
+  uint32_t phase = 0;
+  while (tile < n_tiles) {
+    // split hi / lo, store both copies in the canonical layout
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      float4 hi, lo;
+      hi.x = umma::tf32_rna(x[i].x);
+      hi.y = umma::tf32_rna(x[i].y);
+      hi.z = umma::tf32_rna(x[i].z);
+      hi.w = umma::tf32_rna(x[i].w);
+      lo.x = umma::tf32_rna(x[i].x - hi.x);
+      lo.y = umma::tf32_rna(x[i].y - hi.y);
+      lo.z = umma::tf32_rna(x[i].z - hi.z);
+      lo.w = umma::tf32_rna(x[i].w - hi.w);
+      const int slot = unit_slot(i);
+      sAhi[slot] = hi;
+      sAlo[slot] = lo;
+    }
+    // generic-proxy writes of the operands must be visible to the async proxy the tensor core reads through
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      // hi * hi: K-step ks goes to accumulator ks * NACC / KSTEPS (a chain restarts from zero when the index changes);
+      // lo * hi and hi * lo: one chain in accumulator NACC
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a0 = pass == 1 ? a_lo : a_hi, b0 = pass == 2 ? b_lo : b_hi;
+#pragma unroll 1
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint64_t da = umma::smem_desc(a0 + uint32_t(ks) * 2u * 128u * 16u, 128, 8);
+          const uint64_t db = umma::smem_desc(b0 + uint32_t(ks) * 2u * uint32_t(R) * 16u, R, 8);
+          const int acc = pass == 0 ? ks * NACC / KSTEPS : NACC;
+          const bool first = pass == 0 ? (ks == 0 || (ks - 1) * NACC / KSTEPS != acc) : (pass == 1 && ks == 0);
+          if (HQ_UMMA_DEBUG_ONE_CHAIN) umma::mma_tf32(tmem, da, db, idesc, (pass | ks) ? 1u : 0u);
+          else umma::mma_tf32(tmem + uint32_t(acc * R), da, db, idesc, first ? 0u : 1u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(umma::smem_u32(bar))
+                   : "memory");
+    }
+    const unsigned long long next = tile + gridDim.x;
+    const unsigned long long nbase = next < n_tiles ? spread(next * 128ull) : 0ull;
+    if (next < n_tiles) load_tile(nbase);
+    umma::mbar_wait(umma::smem_u32(bar), phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // epilogue: row `tid` of D = TMEM lane tid (warp w owns lanes 32 w .. 32 w + 31), up to 32 columns per load
+    constexpr int CB = R < 32 ? R : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < R; c0 += CB) {
+      uint32_t v[32], w[32];
+      const uint32_t lane_base = tmem + (uint32_t(warp * 32) << 16) + uint32_t(c0);
+      umma::tmem_ld<CB>(lane_base, v);
+#pragma unroll
+      for (int a = 1; a <= NACC; ++a) {
+        umma::tmem_ld<CB>(lane_base + uint32_t(a * R), w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < CB; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+      }
+#pragma unroll
+      for (int u = 0; u < CB / 4; ++u) {
+        const float4 d = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                                     __uint_as_float(v[4 * u + 3]));
+        const int c = c0 / 4 + u;
+        if (MODEB) {
+          sAhi[c * 128 + tid] = d;
+        } else {
+          store_unit(tbase | rowoff[tid] | dep[2 * c], d);
+        }
+      }
+    }
+    if (MODEB) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < CH; ++i) store_unit(tbase | unit_off(i), sAhi[unit_slot(i)]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();       // the operands and the accumulator may be overwritten
+    tile = next;
+    tbase = nbase;
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(COLS)));
+}
+
+template <int KQ>
+inline size_t umma_smem_bytes() {
+  constexpr int DIM = 1 << KQ, R = 2 * DIM, CH = R / 4;
+  return size_t(2 * CH * 128 + 2 * CH * R) * 16 + size_t(DIM + 128) * 8 + 8 + 16;
+}
+
+// grid of the most recent launch (diagnostics)
+inline unsigned& umma_last_grid() {
+  static unsigned g = 0;
+  return g;
+}
+
+// distinct 128-byte lines one warp-wide access touches when its lanes cover amplitude bits `bits` (16 amplitudes a line)
+inline int umma_lines(const int* bits, int nbits) {
+  int lines = 1;
+  for (int i = 0; i < nbits; ++i)
+    if (bits[i] >= 4) lines *= 2;
+  return lines;
+}
+
+// One dense k = KQ gate on the whole state (n >= KQ + 7).  Bhi / Blo: device pointers to the real form of U split
+// into TF32 hi / lo parts, in canonical units (unit (n, c) at index c * R + n holds Bs[n][4c .. 4c + 3]).
+// mode: -1 = choose the lane mapping from the target positions, 0 = rows, 1 = mixed.
+template <int KQ>
+inline int launch_umma_gate(float2* state, unsigned n_qubits, const UmmaPos& p, const float4* Bhi, const float4* Blo,
+                            cudaStream_t stream, int mode = -1, int ctas_per_sm = 0) {
+  if (n_qubits < unsigned(KQ) + 7u) return int(cudaErrorInvalidValue);
+  const size_t smem = umma_smem_bytes<KQ>();
+  const bool pair16 = p.tpos[0] == 0;
+  if (mode < 0) {
+    // lanes of the two mappings as amplitude bits: 5 (or 3) lowest non-target bits, plus targets 1 and 2
+    int free_bits[5], nf = 0;
+    for (int b = 0, t = 0; nf < 5; ++b) {
+      if (t < KQ && p.tpos[t] == b) {
+        ++t;
+        continue;
+      }
+      free_bits[nf++] = b;
+    }
+    const int mixed[5] = {free_bits[0], free_bits[1], free_bits[2], p.tpos[1], p.tpos[2]};
+    mode = umma_lines(mixed, 5) < umma_lines(free_bits, 5) ? 1 : 0;
+  }
+  void (*kern)(float2*, unsigned long long, UmmaPos, const float4*, const float4*) =
+      mode ? (pair16 ? hq_umma_gate_kernel<KQ, true, true> : hq_umma_gate_kernel<KQ, true, false>)
+           : (pair16 ? hq_umma_gate_kernel<KQ, false, true> : hq_umma_gate_kernel<KQ, false, false>);
+  // per variant: opt in to the shared-memory size once, and ask the runtime how many CTAs really fit on an SM
+  // (registers included) so that the persistent grid is exactly one wave; TMEM columns bound it as well
+  static int resident_all[64][4] = {};      // per device: the shared-memory opt-in is a per-device attribute
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return int(cudaErrorInvalidDevice);
+  int* const resident = resident_all[dev];
+  const int which = (mode ? 2 : 0) + (pair16 ? 1 : 0);
+  if (!resident[which]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    // CTAs that fit on an SM: registers (allocated per warp in units of 8 per thread), shared memory (227 KiB usable,
+    // 1 KiB reserved per CTA), TMEM columns
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return int(e);
+    int occ = 65536 / (((fa.numRegs + 7) & ~7) * 128);
+    const int by_smem = int((227u * 1024u) / (smem + 1024u));
+    if (occ > by_smem) occ = by_smem;
+    if (occ > 512 / umma_tmem_cols<KQ>()) occ = 512 / umma_tmem_cols<KQ>();
+    if (occ < 1) return int(cudaErrorLaunchOutOfResources);
+    resident[which] = occ;
+  }
+  const unsigned long long n_tiles = 1ull << (n_qubits - unsigned(KQ) - 7u);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ctas_per_sm <= 0 || ctas_per_sm > resident[which]) ctas_per_sm = resident[which];
+  unsigned long long grid = (unsigned long long)sms * (unsigned long long)ctas_per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  umma_last_grid() = unsigned(grid);
+  kern<<<unsigned(grid), 128, smem, stream>>>(state, n_tiles, p, Bhi, Blo);
+  return int(cudaGetLastError());
+}
+
+}  // namespace hq

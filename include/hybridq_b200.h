@@ -220,6 +220,16 @@ int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct);
  * 1 = the ring kernel for every pass whose tile has >= 256 units (measurements, tests). */
 int hq_set_ring(int mode);
 
+/* Blackwell tensor-core path for lone dense gates (hq_umma.cuh): a complex64 pass that consists of ONE dense k = 4 or
+ * k = 5 matrix (after in-pass merging) on a state of at least k + 7 qubits runs on `tcgen05.mma kind::tf32` (3xTF32,
+ * operands split hi / lo in registers and staged in shared memory, accumulators in TMEM) instead of the mma.sync
+ * tile-kernel path; same contraction as /root/reference/include/U.h:123-202 for those k.
+ * hq_set_umma: 1 = on (default), 0 = off, negative = query only; returns the previous setting.
+ * hq_umma_launch_count: launches of that kernel by this process.  hq_plan_umma_passes: passes of a plan that qualify. */
+int hq_set_umma(int mode);
+uint64_t hq_umma_launch_count(void);
+int hq_plan_umma_passes(const hq_plan* plan);
+
 /* counters: kernels launched by this library in this process since the last reset */
 uint64_t hq_launch_count(void);
 void hq_launch_count_reset(void);

@@ -491,3 +491,85 @@ def test_lone_scalar_plus_rank_one_gate(hb, oracle, c_oracle):
             assert plan.arithmetic() == {"k4": {"scalar_plus_rank_one": 1}}
             plan.run(st)
             assert np.abs(st.download() - ref).max() <= TOL[ctype]
+
+
+# ------------------------------------------------------------------ tcgen05 lone-gate kernel (hq_umma.cuh)
+@pytest.mark.parametrize("n,pos", [
+    (12, [1, 4, 7, 9, 11]), (12, [0, 1, 2, 3, 4]), (13, [0, 3, 8, 10, 12]), (16, [2, 5, 6, 11, 15]),
+    (16, [1, 2, 3, 14, 15]), (20, [0, 1, 12, 17, 19]), (22, [3, 7, 12, 20, 21]),
+    (11, [0, 1, 2, 3]), (11, [2, 6, 9, 10]), (14, [0, 5, 6, 13]), (18, [1, 2, 16, 17]), (21, [4, 9, 13, 20]),
+])
+def test_tcgen05_lone_gate_parity(hb, oracle, c_oracle, n, pos):
+    """One dense complex64 k = 4 / 5 gate = one pass on the tcgen05 kernel; checked against the oracle, against the
+    mma.sync tile-kernel path it replaces, and (launch counter) that it really ran."""
+    rng = np.random.default_rng(100 * n + len(pos) + pos[0])
+    k = len(pos)
+    U = _haar(rng, k)
+    psi = _rand_state(rng, n, "complex64")
+    perm = rng.permutation(k)                           # matrix bit order need not be ascending
+    gate = (U, [pos[i] for i in perm])
+    ref = oracle.evolve_oracle(psi, [(U.astype("complex64"), gate[1])], c_oracle)
+    plan = hb.Plan([gate], n, "complex64")
+    assert plan.n_umma_passes == 1
+    before = hb.lib.hq_umma_launch_count()
+    st = hb.DeviceState(n, "complex64").upload(psi)
+    plan.run(st)
+    out = st.download()
+    assert hb.lib.hq_umma_launch_count() == before + 1
+    assert np.abs(out - ref).max() <= TOL["complex64"]
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()         # near fp32 accuracy, not merely 1e-6 absolute
+    old = hb.lib.hq_set_umma(0)
+    try:
+        st2 = hb.DeviceState(n, "complex64").upload(psi)
+        plan.run(st2)
+        assert hb.lib.hq_umma_launch_count() == before + 1
+        assert np.abs(st2.download() - out).max() <= 2e-6 * np.abs(ref).max()
+    finally:
+        hb.lib.hq_set_umma(old)
+
+
+def test_tcgen05_path_scope(hb):
+    """Only complex64 passes of one dense k = 4 / 5 matrix on >= k + 7 qubits qualify; everything else keeps its path."""
+    rng = np.random.default_rng(5)
+    U5, U4, U3 = _haar(rng, 5), _haar(rng, 4), _haar(rng, 3)
+    assert hb.Plan([(U5, [0, 1, 2, 3, 4])], 12, "complex128").n_umma_passes == 0
+    assert hb.Plan([(U5, [0, 1, 2, 3, 4])], 11, "complex64").n_umma_passes == 0        # fewer than 128 groups
+    assert hb.Plan([(U3, [0, 1, 2])], 12, "complex64").n_umma_passes == 0
+    assert hb.Plan([(U4, [0, 1, 2, 3]), (U5, [4, 5, 6, 7, 8])], 14, "complex64", hb.PlanOptions(fuse=0)).n_umma_passes == 2
+    assert hb.Plan([(U4, [0, 1, 2, 3])], 14, "complex64", hb.PlanOptions(mma_min_k=0)).n_umma_passes == 0
+
+
+def test_tcgen05_norm_and_error_over_many_gates(hb):
+    """300 random 5-qubit unitaries one after another (each its own tcgen05 pass).  Tensor cores add into their fp32
+    accumulator with truncation, so some norm loss per gate is inherent to both tensor-core paths (measured on B200,
+    profiles/r02/umma_drift.jsonl: -2.0e-5 here, -1.1e-5 on the mma.sync path, after 300 gates); the kernel keeps it
+    there by giving the big hi * hi products short accumulator chains (one chain for everything: -2.0e-4).  The state
+    must stay within the complex64 tolerance of the complex128 run."""
+    rng = np.random.default_rng(77)
+    n = 16
+    gates = []
+    for _ in range(300):
+        pos = sorted(rng.choice(n, size=5, replace=False).tolist())
+        gates.append((_haar(rng, 5), pos))
+    psi = _rand_state(rng, n, "complex128")
+    opts = hb.PlanOptions(fuse=0)
+    plan32 = hb.Plan(gates, n, "complex64", opts)
+    assert plan32.n_umma_passes == 300
+    st32 = hb.DeviceState(n, "complex64").upload(psi.astype("complex64"))
+    before = hb.lib.hq_umma_launch_count()
+    plan32.run(st32)
+    assert hb.lib.hq_umma_launch_count() == before + 300
+    st64 = hb.DeviceState(n, "complex128").upload(psi)
+    hb.Plan(gates, n, "complex128", opts).run(st64)
+    a, b = st32.download(), st64.download()
+    drift = np.linalg.norm(a.astype("complex128")) - 1.0
+    assert abs(drift) < 5e-5, drift
+    assert np.abs(a - b).max() <= TOL["complex64"]
+    old = hb.lib.hq_set_umma(0)
+    try:
+        st = hb.DeviceState(n, "complex64").upload(psi.astype("complex64"))
+        plan32.run(st)
+        drift_mma_sync = np.linalg.norm(st.download().astype("complex128")) - 1.0
+    finally:
+        hb.lib.hq_set_umma(old)
+    assert abs(drift) < 3.0 * abs(drift_mma_sync) + 1e-6, (drift, drift_mma_sync)
