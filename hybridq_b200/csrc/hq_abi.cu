@@ -78,7 +78,7 @@ void fill_gate(hq::GateIn& g, const T* U, const unsigned* pos, unsigned k) {
   for (size_t i = 0; i < e; ++i) g.U[i] = std::complex<double>(double(U[2 * i]), double(U[2 * i + 1]));
 }
 
-int g_use_umma = 1;     // complex64 passes made of one dense k = 4 / 5 matrix go to the tcgen05 kernel (hq_umma.cuh)
+int g_use_umma = 1;     // complex64 passes made of one dense k = 4 .. 6 matrix go to the tcgen05 kernel (hq_umma.cuh)
 std::atomic<uint64_t> g_umma_launches{0};
 int g_use_direct = 1;   // single k <= 2 gate passes go to the shared-memory-free kernel
 
@@ -124,7 +124,7 @@ int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, in
       continue;
     }
     if (g_use_umma && !xg && plan.passes[size_t(p)].umma_off && ph.n_gates == 1 && d_prog) {
-      // measured (profiles/r02): 1.9x (k = 4) / 2.3x (k = 5) the bandwidth of the mma.sync tile-kernel path
+      // measured (profiles/r02): 1.7-1.9x (k = 4), 2.4x (k = 5), 3x (k = 6) the bandwidth of the mma.sync tile-kernel path
       const unsigned L = ph.tile_bits - ph.n_high;
       unsigned pos[8];
       for (unsigned i = 0; i < gd.k; ++i) pos[i] = gd.tpos[i] < L ? gd.tpos[i] : ph.high_pos[gd.tpos[i] - L];

@@ -46,7 +46,7 @@ void set_ring(int mode);
 
 // Direct (no shared memory) single-gate kernel for k <= 3 with every target at or above
 // amplitude bit `V` (see hq_kernels.cu); U is read from kernel parameters.
-// tcgen05 / TMEM kernel for ONE dense complex64 gate, k = 4 or 5, n_qubits >= k + 7 (hq_umma.cuh).  pos ascending;
+// tcgen05 / TMEM kernel for ONE dense complex64 gate, k = 4, 5 or 6, n_qubits >= k + 7 (hq_umma.cuh).  pos ascending;
 // d_operands = device pointer to the B_hi, B_lo blocks written by umma_pack_matrix (hq_plan.h).  Returns a cudaError.
 int launch_umma(void* state, unsigned n_qubits, const unsigned* pos, unsigned k, const void* d_operands, void* stream);
 

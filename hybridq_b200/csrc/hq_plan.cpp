@@ -809,7 +809,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
     }
     plan.passes.push_back(std::move(pi));
   }
-  // ---- tcgen05 operand blocks for passes made of one dense complex64 k = 4 / 5 matrix (hq_umma.cuh) ----
+  // ---- tcgen05 operand blocks for passes made of one dense complex64 k = 4 .. 6 matrix (hq_umma.cuh) ----
   if (dtype == HQ_DTYPE_C64) {
     for (size_t di = 0; di < drafts.size(); ++di) {
       if (merged[di].size() != 1 || !layouts[di][0].mma || layouts[di][0].dr1) continue;

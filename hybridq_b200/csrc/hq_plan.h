@@ -45,7 +45,7 @@ struct PlanOptions {
 struct PassInfo {
   HqPassHeader header;
   std::vector<unsigned> gate_ids;            // indices into the input gate list
-  // tcgen05 path (hq_umma.cuh): a complex64 pass made of ONE dense k = 4 or 5 matrix also carries that matrix as
+  // tcgen05 path (hq_umma.cuh): a complex64 pass made of ONE dense k = 4, 5 or 6 matrix also carries that matrix as
   // TF32 hi / lo operand blocks (B_hi then B_lo, each 2^(2k) * 4 floats) at this program offset; 0 = none
   uint32_t umma_off = 0;
 };
@@ -64,7 +64,7 @@ struct Plan {
 };
 
 // Smallest / largest k of the tcgen05 lone-gate kernel and the state size it needs (128 groups per tile).
-constexpr unsigned UMMA_MIN_K = 4, UMMA_MAX_K = 5, UMMA_ROW_BITS = 7;
+constexpr unsigned UMMA_MIN_K = 4, UMMA_MAX_K = 6, UMMA_ROW_BITS = 7;
 // Real form of a 2^k x 2^k complex matrix as the K-major operand blocks of tcgen05.mma kind::tf32:
 // 16-byte unit (n, c) at index c * R + n holds Bs[n][4c .. 4c + 3], R = 2 * 2^k, Bs[2i + ri][2j + rj] = the real
 // 2 x 2 block of U[i][j]; `hi` = rounded to TF32 (nearest), `lo` = the rounded remainder.  2 * R * R floats are written.

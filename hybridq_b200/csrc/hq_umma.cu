@@ -17,6 +17,7 @@ int launch_umma(void* state, unsigned n_qubits, const unsigned* pos, unsigned k,
   switch (k) {
     case 4: return launch_umma_gate<4>(static_cast<float2*>(state), n_qubits, p, bhi, blo, s);
     case 5: return launch_umma_gate<5>(static_cast<float2*>(state), n_qubits, p, bhi, blo, s);
+    case 6: return launch_umma_gate<6>(static_cast<float2*>(state), n_qubits, p, bhi, blo, s);
     default: return int(cudaErrorInvalidValue);
   }
 }

@@ -120,7 +120,12 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[32]) {
 // TMEM columns of one CTA: up to three hi * hi accumulators and one for the corrections, R columns each (power of two)
 template <int KQ>
 __host__ __device__ constexpr int umma_tmem_cols() {
-  return KQ == 5 ? 256 : (KQ == 4 ? 128 : 64);
+  return KQ == 6 ? 512 : (KQ == 5 ? 256 : (KQ == 4 ? 128 : 64));
+}
+// parts the K dimension is processed in (one A buffer in shared memory per part)
+template <int KQ>
+__host__ __device__ constexpr int umma_ksplit() {
+  return KQ == 6 ? 2 : 1;
 }
 
 // How a warp's lanes are spread over a tile's 16-byte units while it is loaded and stored:
@@ -132,6 +137,10 @@ __host__ __device__ constexpr int umma_tmem_cols() {
 // Both keep every 16-byte shared store / load conflict free (8 consecutive lanes = 8 consecutive rows of one chunk).
 // PAIR16: the lowest target is amplitude bit 0, so a unit is 16 contiguous bytes in memory (one 128-bit access).
 //
+// k = 6 (K = N = 128) does not fit with the whole A tile resident: the K dimension is processed in KSPLIT = 2 halves
+// through one A buffer (fill half, MMAs of that half over the matching K-chunks of the resident B, next half), the
+// accumulators take all 512 TMEM columns, and one CTA per SM runs.
+//
 // state: 2^n interleaved complex64 amplitudes; n_tiles = 2^(n - KQ - 7) tiles of 128 groups
 template <int KQ, bool MODEB, bool PAIR16>
 __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ state, const unsigned long long n_tiles,
@@ -140,20 +149,23 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   constexpr int DIM = 1 << KQ;       // amplitudes per group
   constexpr int R = 2 * DIM;         // reals per group = N = K
   constexpr int CH = R / 4;          // 16-byte K-chunks per row
-  static_assert(KQ >= 3 && KQ <= 5, "tile and TMEM budget are sized for k = 3 .. 5");
+  constexpr int KSPLIT = umma_ksplit<KQ>();
+  constexpr int CHH = CH / KSPLIT;   // K-chunks of the A buffer
+  static_assert(KQ >= 3 && KQ <= 6, "tile and TMEM budget are sized for k = 3 .. 6");
   // The tensor core adds into its fp32 accumulator with truncation (round toward zero); chaining all 3 * R / 8 MMAs
   // through one accumulator shrinks every amplitude by ~7e-7 per gate (measured: norm - 1 = -2.0e-4 after 300 k = 5
-  // gates).  So the big hi * hi products go to NACC separate accumulators (chains of at most 3 K-steps, each starting
-  // from zero), the small lo * hi and hi * lo corrections to one more, and the epilogue adds them with
-  // round-to-nearest FADDs (the scheme of hq_mma.cuh, within the 512-column TMEM budget of two CTAs per SM).
+  // gates).  So the big hi * hi products go to NACC separate accumulators (short chains, each starting from zero),
+  // the small lo * hi and hi * lo corrections to one more, and the epilogue adds them with round-to-nearest FADDs
+  // (the scheme of hq_mma.cuh, within the 512 TMEM columns of an SM).
   constexpr int KSTEPS = R / 8;
+  constexpr int KSTEPS_H = KSTEPS / KSPLIT;
   constexpr int NACC = KSTEPS < HQ_UMMA_NACC ? KSTEPS : HQ_UMMA_NACC;
   constexpr int COLS = umma_tmem_cols<KQ>();
   static_assert((NACC + 1) * R <= COLS, "TMEM columns");
   extern __shared__ __align__(128) unsigned char smem[];
   float4* const sAhi = reinterpret_cast<float4*>(smem);
-  float4* const sAlo = sAhi + CH * 128;
-  float4* const sBhi = sAlo + CH * 128;
+  float4* const sAlo = sAhi + CHH * 128;       // contiguous with sAhi: together they stage the MODEB epilogue
+  float4* const sBhi = sAlo + CHH * 128;
   float4* const sBlo = sBhi + CH * R;
   unsigned long long* const dep = reinterpret_cast<unsigned long long*>(sBlo + CH * R);   // dep[j]: offset of amplitude j
   unsigned long long* const rowoff = dep + DIM;                                            // rowoff[r]: offset of row r
@@ -197,23 +209,21 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   const uint32_t a_hi = umma::smem_u32(sAhi), a_lo = umma::smem_u32(sAlo), b_hi = umma::smem_u32(sBhi), b_lo = umma::smem_u32(sBlo);
   const unsigned long long pair_bit = 1ull << p.tpos[0];
 
-  // unit handled by this thread in iteration i: shared slot and amplitude offset inside the tile
-  auto unit_slot = [&](int i) {
+  // unit handled by this thread in iteration i of a sweep over NCH K-chunks x 128 rows: shared slot = chunk * 128 + row
+  auto unit_slot = [&](int i, int nch) {
     if (!MODEB) return i * 128 + tid;
-    const int q = warp * CH + i;
+    const int q = warp * nch + i;
     return (4 * (q >> 4) + (lane >> 3)) * 128 + 8 * (q & 15) + (lane & 7);
   };
-  auto unit_off = [&](int i) {
-    const int slot = unit_slot(i);
-    return rowoff[slot & 127] | dep[2 * (slot >> 7)];
-  };
-  // one tile's units in registers: every load of a tile is in flight at once, and the loads of the NEXT tile are
-  // issued right after this tile's MMAs so that they overlap the tensor-core work and the epilogue
-  float4 x[CH];
-  auto load_tile = [&](unsigned long long tbase) {
+  // amplitude offset inside the tile of the unit in `slot`, K-chunks counted from chunk0
+  auto unit_off = [&](int slot, int chunk0) { return rowoff[slot & 127] | dep[2 * (chunk0 + (slot >> 7))]; };
+  // the units of one K-part of a tile in registers: all its loads are in flight at once, and the loads of the NEXT
+  // part are issued right after this part's MMAs so that they overlap the tensor-core work and the epilogue
+  float4 x[CHH];
+  auto load_part = [&](unsigned long long tbase, int h) {
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const unsigned long long a = tbase | unit_off(i);
+    for (int i = 0; i < CHH; ++i) {
+      const unsigned long long a = tbase | unit_off(unit_slot(i, CHH), h * CHH);
       if (PAIR16) {
         x[i] = *reinterpret_cast<const float4*>(&state[a]);
       } else {
@@ -232,53 +242,58 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   };
   unsigned long long tile = blockIdx.x;
   unsigned long long tbase = tile < n_tiles ? spread(tile * 128ull) : 0ull;
-  if (tile < n_tiles) load_tile(tbase);
+  if (tile < n_tiles) load_part(tbase, 0);
   uint32_t phase = 0;
   while (tile < n_tiles) {
-    // split hi / lo, store both copies in the canonical layout
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      float4 hi, lo;
-      hi.x = umma::tf32_rna(x[i].x);
-      hi.y = umma::tf32_rna(x[i].y);
-      hi.z = umma::tf32_rna(x[i].z);
-      hi.w = umma::tf32_rna(x[i].w);
-      lo.x = umma::tf32_rna(x[i].x - hi.x);
-      lo.y = umma::tf32_rna(x[i].y - hi.y);
-      lo.z = umma::tf32_rna(x[i].z - hi.z);
-      lo.w = umma::tf32_rna(x[i].w - hi.w);
-      const int slot = unit_slot(i);
-      sAhi[slot] = hi;
-      sAlo[slot] = lo;
-    }
-    // generic-proxy writes of the operands must be visible to the async proxy the tensor core reads through
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      // hi * hi: K-step ks goes to accumulator ks * NACC / KSTEPS (a chain restarts from zero when the index changes);
-      // lo * hi and hi * lo: one chain in accumulator NACC
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a0 = pass == 1 ? a_lo : a_hi, b0 = pass == 2 ? b_lo : b_hi;
-#pragma unroll 1
-        for (int ks = 0; ks < KSTEPS; ++ks) {
-          const uint64_t da = umma::smem_desc(a0 + uint32_t(ks) * 2u * 128u * 16u, 128, 8);
-          const uint64_t db = umma::smem_desc(b0 + uint32_t(ks) * 2u * uint32_t(R) * 16u, R, 8);
-          const int acc = pass == 0 ? ks * NACC / KSTEPS : NACC;
-          const bool first = pass == 0 ? (ks == 0 || (ks - 1) * NACC / KSTEPS != acc) : (pass == 1 && ks == 0);
-          if (HQ_UMMA_DEBUG_ONE_CHAIN) umma::mma_tf32(tmem, da, db, idesc, (pass | ks) ? 1u : 0u);
-          else umma::mma_tf32(tmem + uint32_t(acc * R), da, db, idesc, first ? 0u : 1u);
-        }
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(umma::smem_u32(bar))
-                   : "memory");
-    }
     const unsigned long long next = tile + gridDim.x;
     const unsigned long long nbase = next < n_tiles ? spread(next * 128ull) : 0ull;
-    if (next < n_tiles) load_tile(nbase);
-    umma::mbar_wait(umma::smem_u32(bar), phase);
-    phase ^= 1u;
+#pragma unroll 1
+    for (int h = 0; h < KSPLIT; ++h) {
+      // split hi / lo, store both copies in the canonical layout
+#pragma unroll
+      for (int i = 0; i < CHH; ++i) {
+        float4 hi, lo;
+        hi.x = umma::tf32_rna(x[i].x);
+        hi.y = umma::tf32_rna(x[i].y);
+        hi.z = umma::tf32_rna(x[i].z);
+        hi.w = umma::tf32_rna(x[i].w);
+        lo.x = umma::tf32_rna(x[i].x - hi.x);
+        lo.y = umma::tf32_rna(x[i].y - hi.y);
+        lo.z = umma::tf32_rna(x[i].z - hi.z);
+        lo.w = umma::tf32_rna(x[i].w - hi.w);
+        const int slot = unit_slot(i, CHH);
+        sAhi[slot] = hi;
+        sAlo[slot] = lo;
+      }
+      // generic-proxy writes of the operands must be visible to the async proxy the tensor core reads through
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        // hi * hi: K-step kg goes to accumulator kg * NACC / KSTEPS (a chain restarts from zero when the index changes);
+        // lo * hi and hi * lo: one chain in accumulator NACC
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = pass == 1 ? a_lo : a_hi, b0 = pass == 2 ? b_lo : b_hi;
+#pragma unroll 1
+          for (int ks = 0; ks < KSTEPS_H; ++ks) {
+            const int kg = h * KSTEPS_H + ks;
+            const uint64_t da = umma::smem_desc(a0 + uint32_t(ks) * 2u * 128u * 16u, 128, 8);
+            const uint64_t db = umma::smem_desc(b0 + uint32_t(kg) * 2u * uint32_t(R) * 16u, R, 8);
+            const int acc = pass == 0 ? kg * NACC / KSTEPS : NACC;
+            const bool first = pass == 0 ? (kg == 0 || (kg - 1) * NACC / KSTEPS != acc) : (pass == 1 && kg == 0);
+            if (HQ_UMMA_DEBUG_ONE_CHAIN) umma::mma_tf32(tmem, da, db, idesc, (pass | kg) ? 1u : 0u);
+            else umma::mma_tf32(tmem + uint32_t(acc * R), da, db, idesc, first ? 0u : 1u);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(umma::smem_u32(bar))
+                     : "memory");
+      }
+      if (h + 1 < KSPLIT) load_part(tbase, h + 1);
+      else if (next < n_tiles) load_part(nbase, 0);
+      umma::mbar_wait(umma::smem_u32(bar), phase);      // this part's MMAs are done: the A buffer is free again
+      phase ^= 1u;
+    }
     asm volatile("tcgen05.fence::after_thread_sync;");
     // epilogue: row `tid` of D = TMEM lane tid (warp w owns lanes 32 w .. 32 w + 31), up to 32 columns per load
     constexpr int CB = R < 32 ? R : 32;
@@ -300,7 +315,7 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
                                      __uint_as_float(v[4 * u + 3]));
         const int c = c0 / 4 + u;
         if (MODEB) {
-          sAhi[c * 128 + tid] = d;
+          sAhi[c * 128 + tid] = d;          // CH * 128 units = the A_hi and A_lo buffers together
         } else {
           store_unit(tbase | rowoff[tid] | dep[2 * c], d);
         }
@@ -309,7 +324,10 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
     if (MODEB) {
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < CH; ++i) store_unit(tbase | unit_off(i), sAhi[unit_slot(i)]);
+      for (int i = 0; i < CH; ++i) {
+        const int slot = unit_slot(i, CH);
+        store_unit(tbase | unit_off(slot, 0), sAhi[slot]);
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();       // the operands and the accumulator may be overwritten
@@ -321,8 +339,8 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
 
 template <int KQ>
 inline size_t umma_smem_bytes() {
-  constexpr int DIM = 1 << KQ, R = 2 * DIM, CH = R / 4;
-  return size_t(2 * CH * 128 + 2 * CH * R) * 16 + size_t(DIM + 128) * 8 + 8 + 16;
+  constexpr int DIM = 1 << KQ, R = 2 * DIM, CH = R / 4, CHH = CH / umma_ksplit<KQ>();
+  return size_t(2 * CHH * 128 + 2 * CH * R) * 16 + size_t(DIM + 128) * 8 + 8 + 16;
 }
 
 // grid of the most recent launch (diagnostics)

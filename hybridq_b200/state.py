@@ -84,7 +84,7 @@ class Plan:
         self.n_kernel_gates = lib.hq_plan_num_kernel_gates(self._h)
         self.flops = lib.hq_plan_flops(self._h)
         self.n_passes = lib.hq_plan_num_passes(self._h)
-        # passes (one dense complex64 k = 4 / 5 matrix) that run on the tcgen05 / TMEM kernel (hq_umma.cuh)
+        # passes (one dense complex64 k = 4 .. 6 matrix) that run on the tcgen05 / TMEM kernel (hq_umma.cuh)
         self.n_umma_passes = lib.hq_plan_umma_passes(self._h)
 
     def __del__(self):

@@ -220,8 +220,8 @@ int hq_set_tuning(int nbuf, int ctas_per_sm, int use_direct);
  * 1 = the ring kernel for every pass whose tile has >= 256 units (measurements, tests). */
 int hq_set_ring(int mode);
 
-/* Blackwell tensor-core path for lone dense gates (hq_umma.cuh): a complex64 pass that consists of ONE dense k = 4 or
- * k = 5 matrix (after in-pass merging) on a state of at least k + 7 qubits runs on `tcgen05.mma kind::tf32` (3xTF32,
+/* Blackwell tensor-core path for lone dense gates (hq_umma.cuh): a complex64 pass that consists of ONE dense k = 4, 5
+ * or 6 matrix (after in-pass merging) on a state of at least k + 7 qubits runs on `tcgen05.mma kind::tf32` (3xTF32,
  * operands split hi / lo in registers and staged in shared memory, accumulators in TMEM) instead of the mma.sync
  * tile-kernel path; same contraction as /root/reference/include/U.h:123-202 for those k.
  * hq_set_umma: 1 = on (default), 0 = off, negative = query only; returns the previous setting.

@@ -498,9 +498,11 @@ def test_lone_scalar_plus_rank_one_gate(hb, oracle, c_oracle):
     (12, [1, 4, 7, 9, 11]), (12, [0, 1, 2, 3, 4]), (13, [0, 3, 8, 10, 12]), (16, [2, 5, 6, 11, 15]),
     (16, [1, 2, 3, 14, 15]), (20, [0, 1, 12, 17, 19]), (22, [3, 7, 12, 20, 21]),
     (11, [0, 1, 2, 3]), (11, [2, 6, 9, 10]), (14, [0, 5, 6, 13]), (18, [1, 2, 16, 17]), (21, [4, 9, 13, 20]),
+    (13, [0, 1, 2, 3, 4, 5]), (13, [1, 3, 5, 7, 9, 12]), (15, [0, 2, 7, 8, 13, 14]), (19, [3, 4, 10, 11, 17, 18]),
+    (22, [0, 1, 8, 15, 20, 21]),
 ])
 def test_tcgen05_lone_gate_parity(hb, oracle, c_oracle, n, pos):
-    """One dense complex64 k = 4 / 5 gate = one pass on the tcgen05 kernel; checked against the oracle, against the
+    """One dense complex64 k = 4 / 5 / 6 gate = one pass on the tcgen05 kernel; checked against the oracle, against the
     mma.sync tile-kernel path it replaces, and (launch counter) that it really ran."""
     rng = np.random.default_rng(100 * n + len(pos) + pos[0])
     k = len(pos)
@@ -529,9 +531,12 @@ def test_tcgen05_lone_gate_parity(hb, oracle, c_oracle, n, pos):
 
 
 def test_tcgen05_path_scope(hb):
-    """Only complex64 passes of one dense k = 4 / 5 matrix on >= k + 7 qubits qualify; everything else keeps its path."""
+    """Only complex64 passes of one dense k = 4 .. 6 matrix on >= k + 7 qubits qualify; everything else keeps its path."""
     rng = np.random.default_rng(5)
     U5, U4, U3 = _haar(rng, 5), _haar(rng, 4), _haar(rng, 3)
+    U6 = _haar(rng, 6)
+    assert hb.Plan([(U6, [0, 1, 2, 3, 4, 5])], 13, "complex64").n_umma_passes == 1
+    assert hb.Plan([(U6, [0, 1, 2, 3, 4, 5])], 12, "complex64").n_umma_passes == 0
     assert hb.Plan([(U5, [0, 1, 2, 3, 4])], 12, "complex128").n_umma_passes == 0
     assert hb.Plan([(U5, [0, 1, 2, 3, 4])], 11, "complex64").n_umma_passes == 0        # fewer than 128 groups
     assert hb.Plan([(U3, [0, 1, 2])], 12, "complex64").n_umma_passes == 0

@@ -52,9 +52,9 @@ def drift(n=16, depth=300, k=5):
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "drift":
-        for k in (4, 5):
+        for k in (4, 5, 6):
             drift(16, 300, k)
-            drift(12, 300, k)
+            drift(13, 300, k)
         return
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     rng = np.random.default_rng(3)
@@ -64,8 +64,9 @@ def main():
     cases = [[3, 7, 12, 20, n - 1], [5, 6, 7, 8, 9], [0, 7, 12, 20, n - 2], [0, 1, 12, 20, n - 1], [1, 2, 3, 20, n - 1],
              [0, 1, 2, 3, 4], [n - 5, n - 4, n - 3, n - 2, n - 1], [3, 7, 12, 20], [0, 1, 2, 3], [0, 9, 17, n - 1],
              [n - 4, n - 3, n - 2, n - 1]]
-    for _ in range(6):
-        cases.append(sorted(rng.choice(n, size=5, replace=False).tolist()))
+    cases += [[3, 7, 12, 20, n - 3, n - 1], [0, 7, 12, 20, n - 3, n - 1], [0, 1, 2, 3, 4, 5], [n - 6, n - 5, n - 4, n - 3, n - 2, n - 1]]
+    for k in (5, 5, 5, 6, 6, 4):
+        cases.append(sorted(rng.choice(n, size=k, replace=False).tolist()))
     for pos in cases:
         k = len(pos)
         plan = hb.Plan([(haar_unitary(2 ** k, rng), pos)], n, "complex64")

@@ -91,8 +91,8 @@ static void run(int n, const std::vector<unsigned>& pos, int reps, int mode = -1
         const size_t low = (size_t(1) << pos[size_t(i)]) - 1;
         base = ((base & ~low) << 1) | (base & low);
       }
-      std::complex<double> in[64];
-      size_t idx[64];
+      std::complex<double> in[128];
+      size_t idx[128];
       for (int j = 0; j < DIM; ++j) {
         size_t a = base;
         for (int b = 0; b < KQ; ++b) a |= size_t((j >> b) & 1) << pos[size_t(b)];
@@ -130,9 +130,25 @@ int main(int argc, char** argv) {
     std::vector<unsigned> ps;
     for (int i = 6; i < argc; ++i) ps.push_back(unsigned(atoi(argv[i])));
     if (int(ps.size()) != k) return 2;
+    if (k == 6) run<6>(n, ps, 5, mode, ctas);
     if (k == 5) run<5>(n, ps, 5, mode, ctas);
     if (k == 4) run<4>(n, ps, 5, mode, ctas);
     if (k == 3) run<3>(n, ps, 5, mode, ctas);
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "k6")) {
+    for (int mode = 0; mode < 2; ++mode) {
+      run<6>(14, {1, 4, 7, 9, 12, 13}, 1, mode);
+      run<6>(16, {0, 3, 8, 11, 13, 15}, 1, mode);
+      run<6>(17, {0, 1, 2, 3, 4, 5}, 1, mode);
+      run<6>(20, {2, 5, 6, 11, 17, 19}, 2, mode);
+    }
+    fflush(stdout);
+    run<6>(28, {3, 7, 12, 20, 25, 27}, 5, -1);
+    run<6>(28, {0, 7, 12, 20, 25, 27}, 5, -1);
+    run<6>(28, {0, 1, 2, 3, 4, 5}, 5, 0);
+    run<6>(28, {0, 1, 2, 3, 4, 5}, 5, 1);
+    run<5>(28, {3, 7, 12, 20, 25}, 5, -1);
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "quick")) {
