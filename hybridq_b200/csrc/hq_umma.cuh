@@ -24,6 +24,10 @@
 #ifndef HQ_UMMA_NACC
 #define HQ_UMMA_NACC 3
 #endif
+// Largest K-chunk stride (LBO of the A descriptor, 16-byte units) the shared-memory buffers are sized for.  128 = dense;
+// 129 / 130 / 132 (validated on B200: the no-swizzle layout only needs 16-byte aligned core matrices) skew consecutive
+// chunks by 1 / 2 / 4 bank groups so that a quarter-warp covering 8 / 4 / 2 chunks x 1 / 2 / 4 rows stays conflict free.
+#define HQ_UMMA_LBO_MAX 132
 // timing experiments only (wrong results): 1 = every MMA into accumulator 0, the epilogue unchanged
 #ifndef HQ_UMMA_DEBUG_ONE_CHAIN
 #define HQ_UMMA_DEBUG_ONE_CHAIN 0
@@ -33,6 +37,10 @@ namespace hq {
 
 struct UmmaPos {
   unsigned char tpos[8];     // ascending amplitude-bit positions of matrix bits 0 .. k-1
+  // lane map of the MODEB kernels (umma_lane_map): bit i of cmask set = lane bit i counts K-chunks (else rows);
+  // nchunk = popcount(cmask); lbo = K-chunk stride of the A operand in shared memory, in 16-byte units
+  unsigned char cmask, nchunk;
+  unsigned short lbo;
 };
 
 namespace umma {
@@ -93,12 +101,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
-// fp32 -> TF32, round to nearest (ties away): unlike truncation it leaves no bias for the norm to drift on
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// fp32 -> TF32, round to nearest (ties away): unlike truncation it leaves no bias for the norm to drift on.
+// Integer add + mask = what cvt.rna.tf32.f32 does for finite values, in 2 instructions instead of the 4-5 ptxas
+// emits for the cvt (inf / nan guard); a state vector holds no inf / nan worth preserving.
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 // 16 consecutive columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -122,19 +128,30 @@ template <int KQ>
 __host__ __device__ constexpr int umma_tmem_cols() {
   return KQ == 6 ? 512 : (KQ == 5 ? 256 : (KQ == 4 ? 128 : 64));
 }
+// how many parts ahead the global loads run (register buffers): measured on B200 (profiles/r02/umma_gate_test_*.log),
+// two help k = 6 (+12 %, one CTA per SM) and k = 4 (+5 %), not k = 5 (registers: 255 instead of 190 per thread)
+template <int KQ, bool MODEB>
+__host__ __device__ constexpr int umma_prefetch() {
+#ifdef HQ_UMMA_PREFETCH
+  return HQ_UMMA_PREFETCH;
+#else
+  return (KQ == 5 || (KQ == 6 && MODEB)) ? 1 : 2;      // k = 6 with the memory-order lane map would spill with two buffers
+#endif
+}
 // parts the K dimension is processed in (one A buffer in shared memory per part)
 template <int KQ>
 __host__ __device__ constexpr int umma_ksplit() {
   return KQ == 6 ? 2 : 1;
 }
 
-// How a warp's lanes are spread over a tile's 16-byte units while it is loaded and stored:
-//   rows   (MODEB = false): lane = 5 low row bits; thread r owns row r, iteration i handles K-chunk i.  Best when the
-//                           low amplitude bits are not targets (consecutive groups are contiguous in memory).
-//   mixed  (MODEB = true):  lane = 3 low row bits x 2 low K-chunk bits, for gates whose targets include low bits
-//                           (then consecutive K-chunks are the contiguous ones).  The epilogue is staged through the
-//                           (free) A_hi buffer so that the stores use the same mapping.
-// Both keep every 16-byte shared store / load conflict free (8 consecutive lanes = 8 consecutive rows of one chunk).
+// How a warp's lanes are spread over a tile's 16-byte units (row r, K-chunk c) while it is loaded and stored:
+//   MODEB = false: lane = 5 low row bits; thread r owns row r, iteration i handles K-chunk i.  Used when the five lowest
+//                  amplitude bits outside the lowest target are all non-targets (consecutive groups are contiguous).
+//   MODEB = true:  the lane bits follow the memory order of the tile: lane bit i is the i-th lowest amplitude bit among
+//                  row bits and K-chunk bits (targets 1 ..), so that the 8 lanes of a quarter-warp -- the unit in which
+//                  128-bit accesses are coalesced -- read one contiguous run whatever the targets are.  The chunk stride
+//                  of the A operand is skewed (UmmaPos::lbo) to keep the 16-byte shared accesses of such a quarter-warp
+//                  conflict free, and the epilogue is staged through the (free) A buffers to use the same mapping.
 // PAIR16: the lowest target is amplitude bit 0, so a unit is 16 contiguous bytes in memory (one 128-bit access).
 //
 // k = 6 (K = N = 128) does not fit with the whole A tile resident: the K dimension is processed in KSPLIT = 2 halves
@@ -151,6 +168,10 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   constexpr int CH = R / 4;          // 16-byte K-chunks per row
   constexpr int KSPLIT = umma_ksplit<KQ>();
   constexpr int CHH = CH / KSPLIT;   // K-chunks of the A buffer
+  constexpr int PF = umma_prefetch<KQ, MODEB>();   // parts the loads run ahead
+  constexpr int LBO_MAX = HQ_UMMA_LBO_MAX;
+  const int LBO = MODEB ? int(p.lbo) : 128;
+  auto phys = [&](int slot) { return (slot >> 7) * LBO + (slot & 127); };   // shared index of logical slot chunk * 128 + row
   static_assert(KQ >= 3 && KQ <= 6, "tile and TMEM budget are sized for k = 3 .. 6");
   // The tensor core adds into its fp32 accumulator with truncation (round toward zero); chaining all 3 * R / 8 MMAs
   // through one accumulator shrinks every amplitude by ~7e-7 per gate (measured: norm - 1 = -2.0e-4 after 300 k = 5
@@ -164,8 +185,8 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   static_assert((NACC + 1) * R <= COLS, "TMEM columns");
   extern __shared__ __align__(128) unsigned char smem[];
   float4* const sAhi = reinterpret_cast<float4*>(smem);
-  float4* const sAlo = sAhi + CHH * 128;       // contiguous with sAhi: together they stage the MODEB epilogue
-  float4* const sBhi = sAlo + CHH * 128;
+  float4* const sAlo = sAhi + CHH * LBO_MAX;       // contiguous with sAhi: together they stage the MODEB epilogue
+  float4* const sBhi = sAlo + CHH * LBO_MAX;
   float4* const sBlo = sBhi + CH * R;
   unsigned long long* const dep = reinterpret_cast<unsigned long long*>(sBlo + CH * R);   // dep[j]: offset of amplitude j
   unsigned long long* const rowoff = dep + DIM;                                            // rowoff[r]: offset of row r
@@ -210,25 +231,44 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   const unsigned long long pair_bit = 1ull << p.tpos[0];
 
   // unit handled by this thread in iteration i of a sweep over NCH K-chunks x 128 rows: shared slot = chunk * 128 + row
+  // MODEB: this lane's share of the chunk and row numbers (lane bits compacted by cmask), the rest comes from
+  // q = warp * nch + i: row bits first (2 + A of them), then chunk bits
+  const int A = MODEB ? int(p.nchunk) : 0;
+  int c_lane = 0, r_lane = 0;
+  if (MODEB) {
+    int ci = 0, ri = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      if ((p.cmask >> b) & 1) c_lane |= ((lane >> b) & 1) << ci++;
+      else r_lane |= ((lane >> b) & 1) << ri++;
+    }
+  }
   auto unit_slot = [&](int i, int nch) {
     if (!MODEB) return i * 128 + tid;
     const int q = warp * nch + i;
-    return (4 * (q >> 4) + (lane >> 3)) * 128 + 8 * (q & 15) + (lane & 7);
+    const int r = ((q & ((4 << A) - 1)) << (5 - A)) | r_lane, c = ((q >> (2 + A)) << A) | c_lane;
+    return c * 128 + r;
   };
   // amplitude offset inside the tile of the unit in `slot`, K-chunks counted from chunk0
   auto unit_off = [&](int slot, int chunk0) { return rowoff[slot & 127] | dep[2 * (chunk0 + (slot >> 7))]; };
-  // the units of one K-part of a tile in registers: all its loads are in flight at once, and the loads of the NEXT
-  // part are issued right after this part's MMAs so that they overlap the tensor-core work and the epilogue
-  float4 x[CHH];
-  auto load_part = [&](unsigned long long tbase, int h) {
+  // The units of one K-part of a tile live in registers: all loads of a part are in flight at once.  With PF = 2 two
+  // register buffers alternate, so that while part s is converted, multiplied and written back, the loads of parts
+  // s + 1 and s + 2 are outstanding (those of s + 2 are issued into the buffer of s as soon as it has been stored to
+  // shared memory): up to 2 x 32 KiB per CTA in flight.  With PF = 1 there is one buffer and one part in flight.  Part s of this CTA = K-part s % KSPLIT of tile blockIdx.x + (s / KSPLIT) * gridDim.x.
+  auto part_tile = [&](unsigned long long sidx) { return (unsigned long long)blockIdx.x + (sidx / KSPLIT) * gridDim.x; };
+  auto load_part = [&](float4 (&buf)[CHH], unsigned long long sidx) {
+    const unsigned long long t = part_tile(sidx);
+    if (t >= n_tiles) return;
+    const unsigned long long tb = spread(t * 128ull);
+    const int h = int(sidx % KSPLIT);
 #pragma unroll
     for (int i = 0; i < CHH; ++i) {
-      const unsigned long long a = tbase | unit_off(unit_slot(i, CHH), h * CHH);
+      const unsigned long long a = tb | unit_off(unit_slot(i, CHH), h * CHH);
       if (PAIR16) {
-        x[i] = *reinterpret_cast<const float4*>(&state[a]);
+        buf[i] = *reinterpret_cast<const float4*>(&state[a]);
       } else {
         const float2 x0 = state[a], x1 = state[a | pair_bit];
-        x[i] = make_float4(x0.x, x0.y, x1.x, x1.y);
+        buf[i] = make_float4(x0.x, x0.y, x1.x, x1.y);
       }
     }
   };
@@ -240,60 +280,59 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
       state[a | pair_bit] = make_float2(v.z, v.w);
     }
   };
-  unsigned long long tile = blockIdx.x;
-  unsigned long long tbase = tile < n_tiles ? spread(tile * 128ull) : 0ull;
-  if (tile < n_tiles) load_part(tbase, 0);
   uint32_t phase = 0;
-  while (tile < n_tiles) {
-    const unsigned long long next = tile + gridDim.x;
-    const unsigned long long nbase = next < n_tiles ? spread(next * 128ull) : 0ull;
-#pragma unroll 1
-    for (int h = 0; h < KSPLIT; ++h) {
-      // split hi / lo, store both copies in the canonical layout
+  auto step = [&](float4 (&x)[CHH], unsigned long long sidx) {
+    const int h = int(sidx % KSPLIT);
+    // split hi / lo, store both copies in the canonical layout
 #pragma unroll
-      for (int i = 0; i < CHH; ++i) {
-        float4 hi, lo;
-        hi.x = umma::tf32_rna(x[i].x);
-        hi.y = umma::tf32_rna(x[i].y);
-        hi.z = umma::tf32_rna(x[i].z);
-        hi.w = umma::tf32_rna(x[i].w);
-        lo.x = umma::tf32_rna(x[i].x - hi.x);
-        lo.y = umma::tf32_rna(x[i].y - hi.y);
-        lo.z = umma::tf32_rna(x[i].z - hi.z);
-        lo.w = umma::tf32_rna(x[i].w - hi.w);
-        const int slot = unit_slot(i, CHH);
-        sAhi[slot] = hi;
-        sAlo[slot] = lo;
-      }
-      // generic-proxy writes of the operands must be visible to the async proxy the tensor core reads through
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        // hi * hi: K-step kg goes to accumulator kg * NACC / KSTEPS (a chain restarts from zero when the index changes);
-        // lo * hi and hi * lo: one chain in accumulator NACC
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = pass == 1 ? a_lo : a_hi, b0 = pass == 2 ? b_lo : b_hi;
-#pragma unroll 1
-          for (int ks = 0; ks < KSTEPS_H; ++ks) {
-            const int kg = h * KSTEPS_H + ks;
-            const uint64_t da = umma::smem_desc(a0 + uint32_t(ks) * 2u * 128u * 16u, 128, 8);
-            const uint64_t db = umma::smem_desc(b0 + uint32_t(kg) * 2u * uint32_t(R) * 16u, R, 8);
-            const int acc = pass == 0 ? kg * NACC / KSTEPS : NACC;
-            const bool first = pass == 0 ? (kg == 0 || (kg - 1) * NACC / KSTEPS != acc) : (pass == 1 && kg == 0);
-            if (HQ_UMMA_DEBUG_ONE_CHAIN) umma::mma_tf32(tmem, da, db, idesc, (pass | kg) ? 1u : 0u);
-            else umma::mma_tf32(tmem + uint32_t(acc * R), da, db, idesc, first ? 0u : 1u);
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(umma::smem_u32(bar))
-                     : "memory");
-      }
-      if (h + 1 < KSPLIT) load_part(tbase, h + 1);
-      else if (next < n_tiles) load_part(nbase, 0);
-      umma::mbar_wait(umma::smem_u32(bar), phase);      // this part's MMAs are done: the A buffer is free again
-      phase ^= 1u;
+    for (int i = 0; i < CHH; ++i) {
+      float4 hi, lo;
+      hi.x = umma::tf32_rna(x[i].x);
+      hi.y = umma::tf32_rna(x[i].y);
+      hi.z = umma::tf32_rna(x[i].z);
+      hi.w = umma::tf32_rna(x[i].w);
+      lo.x = umma::tf32_rna(x[i].x - hi.x);
+      lo.y = umma::tf32_rna(x[i].y - hi.y);
+      lo.z = umma::tf32_rna(x[i].z - hi.z);
+      lo.w = umma::tf32_rna(x[i].w - hi.w);
+      const int slot = unit_slot(i, CHH);
+      sAhi[phys(slot)] = hi;
+      sAlo[phys(slot)] = lo;
     }
+    // generic-proxy writes of the operands must be visible to the async proxy the tensor core reads through
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      // hi * hi: K-step kg goes to accumulator kg * NACC / KSTEPS (a chain restarts from zero when the index changes);
+      // lo * hi and hi * lo: one chain in accumulator NACC, interleaved with the hi * hi MMAs so that the tensor pipe
+      // always has an independent MMA to run while a chained one waits for its accumulator
+#pragma unroll 1
+      for (int ks = 0; ks < KSTEPS_H; ++ks) {
+        const int kg = h * KSTEPS_H + ks;
+        const uint32_t a_off = uint32_t(ks) * 2u * uint32_t(LBO) * 16u, b_off = uint32_t(kg) * 2u * uint32_t(R) * 16u;
+        const uint64_t da_hi = umma::smem_desc(a_hi + a_off, LBO, 8), da_lo = umma::smem_desc(a_lo + a_off, LBO, 8);
+        const uint64_t db_hi = umma::smem_desc(b_hi + b_off, R, 8), db_lo = umma::smem_desc(b_lo + b_off, R, 8);
+        const int acc = kg * NACC / KSTEPS;
+        const bool first = kg == 0 || (kg - 1) * NACC / KSTEPS != acc;
+        if (HQ_UMMA_DEBUG_ONE_CHAIN) {
+          umma::mma_tf32(tmem, da_hi, db_hi, idesc, kg ? 1u : 0u);
+          umma::mma_tf32(tmem, da_lo, db_hi, idesc, 1u);
+          umma::mma_tf32(tmem, da_hi, db_lo, idesc, 1u);
+        } else {
+          umma::mma_tf32(tmem + uint32_t(acc * R), da_hi, db_hi, idesc, first ? 0u : 1u);
+          umma::mma_tf32(tmem + uint32_t(NACC * R), da_lo, db_hi, idesc, kg ? 1u : 0u);
+          umma::mma_tf32(tmem + uint32_t(NACC * R), da_hi, db_lo, idesc, 1u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(umma::smem_u32(bar))
+                   : "memory");
+    }
+    load_part(x, sidx + PF);                           // the registers of this part are free: fetch a later part into them
+    umma::mbar_wait(umma::smem_u32(bar), phase);      // this part's MMAs are done: the A buffer is free again
+    phase ^= 1u;
+    if (h + 1 < KSPLIT) return;
+    const unsigned long long tbase = spread(part_tile(sidx) * 128ull);
     asm volatile("tcgen05.fence::after_thread_sync;");
     // epilogue: row `tid` of D = TMEM lane tid (warp w owns lanes 32 w .. 32 w + 31), up to 32 columns per load
     constexpr int CB = R < 32 ? R : 32;
@@ -315,7 +354,7 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
                                      __uint_as_float(v[4 * u + 3]));
         const int c = c0 / 4 + u;
         if (MODEB) {
-          sAhi[c * 128 + tid] = d;          // CH * 128 units = the A_hi and A_lo buffers together
+          sAhi[c * LBO + tid] = d;          // CH * LBO units = the A_hi and A_lo buffers together
         } else {
           store_unit(tbase | rowoff[tid] | dep[2 * c], d);
         }
@@ -326,13 +365,28 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         const int slot = unit_slot(i, CH);
-        store_unit(tbase | unit_off(slot, 0), sAhi[slot]);
+        store_unit(tbase | unit_off(slot, 0), sAhi[phys(slot)]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();       // the operands and the accumulator may be overwritten
-    tile = next;
-    tbase = nbase;
+  };
+  if (PF == 2) {
+    float4 xa[CHH], xb[CHH];
+    load_part(xa, 0);
+    load_part(xb, 1);
+#pragma unroll 1
+    for (unsigned long long sidx = 0;; sidx += 2) {
+      if (part_tile(sidx) >= n_tiles) break;
+      step(xa, sidx);
+      if (part_tile(sidx + 1) >= n_tiles) break;
+      step(xb, sidx + 1);
+    }
+  } else {
+    float4 xa[CHH];
+    load_part(xa, 0);
+#pragma unroll 1
+    for (unsigned long long sidx = 0; part_tile(sidx) < n_tiles; ++sidx) step(xa, sidx);
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(COLS)));
 }
@@ -340,7 +394,7 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
 template <int KQ>
 inline size_t umma_smem_bytes() {
   constexpr int DIM = 1 << KQ, R = 2 * DIM, CH = R / 4, CHH = CH / umma_ksplit<KQ>();
-  return size_t(2 * CHH * 128 + 2 * CH * R) * 16 + size_t(DIM + 128) * 8 + 8 + 16;
+  return size_t(2 * CHH * HQ_UMMA_LBO_MAX + 2 * CH * R) * 16 + size_t(DIM + 128) * 8 + 8 + 16;
 }
 
 // grid of the most recent launch (diagnostics)
@@ -349,35 +403,63 @@ inline unsigned& umma_last_grid() {
   return g;
 }
 
-// distinct 128-byte lines one warp-wide access touches when its lanes cover amplitude bits `bits` (16 amplitudes a line)
-inline int umma_lines(const int* bits, int nbits) {
-  int lines = 1;
-  for (int i = 0; i < nbits; ++i)
-    if (bits[i] >= 4) lines *= 2;
-  return lines;
+// Lane map in memory order (see the kernel): scan the amplitude bits upwards, skip the lowest target (it lives inside a
+// unit), and give the next five bits to the lanes -- a target is the next K-chunk bit (at most max_chunk_bits of them),
+// anything else the next row bit.  The quarter-warp (lane bits 0 .. 2) then spans 2^a chunks x 2^(3-a) rows, which are
+// conflict free in shared memory when consecutive chunks are 2^(3-a) bank groups apart: lbo = 128 + 2^(3-a) (128 if a = 0).
+inline void umma_lane_map(UmmaPos& p, int k, int max_chunk_bits) {
+  int lane_i = 0, chunks = 0, quarter_chunks = 0, t = 1;
+  p.cmask = 0;
+  for (int b = 0; lane_i < 5; ++b) {
+    if (b == int(p.tpos[0])) continue;
+    if (t < k && b == int(p.tpos[t])) {
+      ++t;
+      if (chunks >= max_chunk_bits) continue;      // a higher chunk bit: left to the iterations
+      p.cmask |= (unsigned char)(1u << lane_i);
+      ++chunks;
+      if (lane_i < 3) ++quarter_chunks;
+    }
+    ++lane_i;
+  }
+  p.nchunk = (unsigned char)chunks;
+  p.lbo = (unsigned short)(quarter_chunks ? 128 + (8 >> quarter_chunks) : 128);
 }
 
 // One dense k = KQ gate on the whole state (n >= KQ + 7).  Bhi / Blo: device pointers to the real form of U split
 // into TF32 hi / lo parts, in canonical units (unit (n, c) at index c * R + n holds Bs[n][4c .. 4c + 3]).
-// mode: -1 = choose the lane mapping from the target positions, 0 = rows, 1 = mixed.
+// mode: -1 = lane mapping from the target positions, 0 = rows only, 1 = memory-order map even when it equals rows.
 template <int KQ>
-inline int launch_umma_gate(float2* state, unsigned n_qubits, const UmmaPos& p, const float4* Bhi, const float4* Blo,
+inline int launch_umma_gate(float2* state, unsigned n_qubits, const UmmaPos& p_in, const float4* Bhi, const float4* Blo,
                             cudaStream_t stream, int mode = -1, int ctas_per_sm = 0) {
   if (n_qubits < unsigned(KQ) + 7u) return int(cudaErrorInvalidValue);
   const size_t smem = umma_smem_bytes<KQ>();
-  const bool pair16 = p.tpos[0] == 0;
+  const bool pair16 = p_in.tpos[0] == 0;
+  constexpr int CHH_BITS = KQ - 1 - (umma_ksplit<KQ>() == 2 ? 1 : 0);      // log2 of the K-chunks in the A buffer
+  UmmaPos p = p_in;
+  umma_lane_map(p, KQ, CHH_BITS);
   if (mode < 0) {
-    // lanes of the two mappings as amplitude bits: 5 (or 3) lowest non-target bits, plus targets 1 and 2
-    int free_bits[5], nf = 0;
-    for (int b = 0, t = 0; nf < 5; ++b) {
-      if (t < KQ && p.tpos[t] == b) {
-        ++t;
-        continue;
+    // 128-byte lines one warp-wide access touches (16 amplitudes a line) with the lanes on the five lowest row bits
+    // versus on the five lowest bits in memory order; the memory-order kernels cost ~10 % (staged epilogue, registers;
+    // k = 6: one register buffer instead of two), so they must save at least half (k = 6: three quarters) of the lines
+    int lines_rows = 1, lines_mem = 1, seen = 0, rows_seen = 0;
+    for (int b = 0, t = 0; rows_seen < 5; ++b) {
+      const bool is_target = t < KQ && b == int(p.tpos[t]);
+      if (is_target) ++t;
+      if (!is_target) {
+        ++rows_seen;
+        if (b >= 4) lines_rows *= 2;
       }
-      free_bits[nf++] = b;
+      if (b != int(p.tpos[0]) && seen < 5) {
+        ++seen;
+        if (b >= 4) lines_mem *= 2;
+      }
     }
-    const int mixed[5] = {free_bits[0], free_bits[1], free_bits[2], p.tpos[1], p.tpos[2]};
-    mode = umma_lines(mixed, 5) < umma_lines(free_bits, 5) ? 1 : 0;
+    mode = (p.nchunk && lines_mem * (KQ == 6 ? 4 : 2) <= lines_rows) ? 1 : 0;
+  }
+  if (mode == 0) {          // rows only (forced, or nothing to gain)
+    p.cmask = 0;
+    p.nchunk = 0;
+    p.lbo = 128;
   }
   void (*kern)(float2*, unsigned long long, UmmaPos, const float4*, const float4*) =
       mode ? (pair16 ? hq_umma_gate_kernel<KQ, true, true> : hq_umma_gate_kernel<KQ, true, false>)
