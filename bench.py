@@ -540,7 +540,7 @@ class SingleGpuRunner:
 
     def extra_roofline(self, peak):
         """Lone 1-/2-/3-qubit gate launches (the north star's >= 70 % HBM target), lone k = 4..6 gates on the
-        tensor cores, which arithmetic the fused passes ran on, and the same circuit with complex64 k = 3 matrices on
+        tensor cores (tcgen05 kernel and the mma.sync path beside it), which arithmetic the fused passes ran on, and the same circuit with complex64 k = 3 matrices on
         the tensor cores (3xTF32 mma.sync, the round-1 default), all measured live with CUDA events."""
         C = load_circuits()
         hb = self.hb
@@ -560,14 +560,34 @@ class SingleGpuRunner:
         worst = min(single.values())
         out["single_gate"] = {"kernel": "hq_direct_kernel (k <= 3, no shared memory)", "GBps": single, "min_GBps": worst,
                               "min_frac_of_measured_peak": worst / peak, "min_frac_of_8TBs": worst / 8000.0}
-        tensor = {}
+        # lone dense k = 4..6 gates: the tcgen05 / TMEM kernel (hq_umma.cuh, default) and the mma.sync tile-kernel
+        # path it replaced, same gates, plus the five lowest bits as the worst case for coalescing
+        def lone_plan(plan, reps):
+            for _ in range(2):
+                plan.run(self.state)
+            return bytes_pass / (cuda_time_ms(lambda: plan.run(self.state), reps) * 1e-3) / 1e9
+
+        tensor, tensor_old, frac = {}, {}, {}
+        umma_before = hb.lib.hq_umma_launch_count()
         for k in (4, 5, 6):
-            pos = sorted(int(x) for x in rng.permutation(self.n)[:k])
-            tensor[f"k{k}_random_bits"] = lone(k, pos, 4)
-        out["tensor_core_gates"] = {"kernel": "hq_tile_kernel, mma.sync 3xTF32 gate path (complex64 k >= 4)", "GBps": tensor,
-                                    "tflops_3xtf32": {f"k{k}": 3 * 8.0 * 2 ** k * 2 ** self.n /
-                                                      (bytes_pass / (tensor[f"k{k}_random_bits"] * 1e9)) / 1e12
-                                                      for k in (4, 5, 6)}}
+            for name, pos in ((f"k{k}_random_bits", sorted(int(x) for x in rng.permutation(self.n)[:k])),
+                              (f"k{k}_lowest_bits", list(range(k)))):
+                plan = hb.Plan([(C.haar_unitary(2 ** k, rng), pos)], self.n, CTYPE)
+                tensor[name] = lone_plan(plan, 4)
+                frac[name] = tensor[name] / peak
+                old = hb.lib.hq_set_umma(0)
+                try:
+                    tensor_old[name] = lone_plan(plan, 2)
+                finally:
+                    hb.lib.hq_set_umma(old)
+        out["tensor_core_gates"] = {
+            "kernel": "hq_umma_gate_kernel: tcgen05.mma kind::tf32 (3xTF32), accumulators in TMEM, one gate per pass "
+                      "(complex64 k = 4..6)",
+            "GBps": tensor, "frac_of_measured_peak": frac,
+            "launches": int(hb.lib.hq_umma_launch_count() - umma_before),
+            "mma_sync_path_GBps": tensor_old,
+            "tflops_3xtf32": {f"k{k}": 3 * 8.0 * 2 ** k * 2 ** self.n /
+                              (bytes_pass / (tensor[f"k{k}_random_bits"] * 1e9)) / 1e12 for k in (4, 5, 6)}}
         kms = self.kernel_time_ms(reps=1)
         out["fused_fp32_tflops"] = self.plan.flops / (kms * 1e-3) / 1e12
         out["fp32_tflops_nominal_peak"] = 148 * 128 * 2 * 1.965e9 / 1e12
