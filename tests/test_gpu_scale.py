@@ -111,6 +111,34 @@ def test_config3_k_sweep_n28_complex128_vs_reference_core(hb, oracle, ref_core):
     assert _device_max_abs_diff(lone, ref) <= TOL[ctype]
 
 
+def test_big_gates_n28_complex64_tcgen05_vs_reference_core(hb, oracle, ref_core):
+    """SURVEY 8(a2) at scale on the tcgen05 path: dense k = 4, 5, 6 gates (ksweep_circuit, the config-3 generator) on a
+    2^28 complex64 state, one pass per gate = one launch of hq_umma_gate_kernel each, plus gates on the lowest bits
+    (memory-order lane map, 128-bit units); FULL vector against the reference's compiled core."""
+    from hybridq_b200.circuits import ksweep_circuit, to_positions, haar_unitary
+    n, ctype = 28, "complex64"
+    lowered = []
+    for k, cnt in ((4, 3), (5, 3), (6, 2)):
+        lowered += to_positions(ksweep_circuit(n, k, n_gates=cnt), qubits=list(range(n)))[0]
+    rng = np.random.default_rng(28)
+    for pos in ([0, 1, 2, 3], [0, 1, 2, 3, 4], [1, 2, 3, 4, 5, 27], [0, 2, 3, 26, 27]):
+        lowered.append((haar_unitary(2 ** len(pos), rng), pos))
+    st = hb.DeviceState(n, ctype).init_random(seed=5)
+    psi0 = st.download()
+    plan = hb.Plan(lowered, n, ctype, hb.PlanOptions(fuse=0))
+    assert plan.n_umma_passes == len(lowered) == 12
+    before = hb.lib.hq_umma_launch_count()
+    plan.run(st)
+    st.sync()
+    assert hb.lib.hq_umma_launch_count() == before + 12
+    ref = oracle.evolve_ref(psi0, [(U.astype(ctype), p) for U, p in lowered], ref_core)
+    del psi0
+    err = _device_max_abs_diff(st, ref)
+    assert err <= TOL[ctype], err
+    assert err <= 1e-8, err                   # 2^-14 amplitudes: twelve gates stay at the 1e-9 level
+    assert abs(st.norm2() - 1) < 2e-6
+
+
 # ------------------------------------------------------------------------------ config 5: density matrices
 def test_dm_10_and_12_qubits_vs_reference(hb, oracle, ref_core, golden):
     """2^20 and 2^24 superkets: the lowered circuits come from the reference's dm front-end
