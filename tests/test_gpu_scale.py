@@ -139,6 +139,33 @@ def test_big_gates_n28_complex64_tcgen05_vs_reference_core(hb, oracle, ref_core)
     assert abs(st.norm2() - 1) < 2e-6
 
 
+def test_big_gates_n30_complex64_round_trip(hb):
+    """BASELINE size (n = 30, 8 GiB state), size-independent property: U then U^dagger on the tcgen05 path gives the
+    state back (k = 4, 5, 6; spread targets and the lowest bits), and the norm is kept."""
+    from hybridq_b200.circuits import haar_unitary
+    import torch
+    n, ctype = 30, "complex64"
+    rng = np.random.default_rng(30)
+    st = hb.DeviceState(n, ctype).init_random(seed=9)
+    ref = st.copy()
+    gates = []
+    for pos in ([3, 9, 17, 29], [0, 1, 2, 3], [2, 8, 15, 22, 28], [0, 1, 2, 3, 4], [1, 6, 13, 19, 24, 29], [0, 1, 2, 3, 4, 5]):
+        U = haar_unitary(2 ** len(pos), rng)
+        gates += [(U, pos), (U.conj().T, pos)]
+    plan = hb.Plan(gates, n, ctype, hb.PlanOptions(fuse=0, merge_max_k=0))
+    assert plan.n_umma_passes == len(gates)
+    before = hb.lib.hq_umma_launch_count()
+    plan.run(st)
+    st.sync()
+    assert hb.lib.hq_umma_launch_count() == before + len(gates)
+    worst = 0.0
+    a, b = st.tensor, ref.tensor
+    for lo in range(0, a.numel(), 1 << 27):
+        worst = max(worst, float((a[lo:lo + (1 << 27)] - b[lo:lo + (1 << 27)]).abs().max()))
+    assert worst <= 1e-8, worst                       # amplitudes ~ 3e-5: relative 3e-4 would already fail
+    assert abs(st.norm2() - 1) < 2e-6
+
+
 # ------------------------------------------------------------------------------ config 5: density matrices
 def test_dm_10_and_12_qubits_vs_reference(hb, oracle, ref_core, golden):
     """2^20 and 2^24 superkets: the lowered circuits come from the reference's dm front-end
