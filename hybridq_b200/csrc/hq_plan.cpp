@@ -567,14 +567,24 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
 
   // ---- greedy fusion: a gate joins the open pass if it touches no bit a deferred gate
   // touches and the union of target bits still fits in a tile with runs >= fuse_min_run.
+  // A dense complex64 gate of UMMA_MIN_K .. UMMA_MAX_K qubits is cheaper as a pass of its own on the tcgen05 kernel
+  // (hq_umma.cuh: 2.7 / 3.6 / 3.9 ms at n = 30 for k = 4 / 5 / 6 whatever was multiplied into it) than as one more
+  // matrix of a tile pass on the mma.sync path (5.3 ms and up per matrix): such a "solo" gate opens its own pass, which
+  // then only admits gates acting inside its qubits -- they are multiplied into its matrix below (so the rule is off
+  // when the caller switched merging off, merge_max_k = 0).
+  const int fuse_mma_min_k = opts.mma_min_k < 0 ? default_mma_min_k(dtype) : opts.mma_min_k;
+  auto is_solo = [&](const Canon& g) {
+    return opts.fuse && opts.merge_max_k != 0 && dtype == HQ_DTYPE_C64 && fuse_mma_min_k >= 2 && int(g.k) >= fuse_mma_min_k && g.k >= UMMA_MIN_K &&
+           g.k <= UMMA_MAX_K && g.k <= unsigned(HQ_MMA_MAX_K) && !g.dr1 && n >= g.k + UMMA_ROW_BITS;
+  };
   std::vector<bool> done(canon.size(), false);
   size_t first = 0;
-  struct Draft { std::vector<unsigned> ids; std::vector<unsigned> bits; };
+  struct Draft { std::vector<unsigned> ids; std::vector<unsigned> bits; bool solo = false; };
   std::vector<Draft> drafts;
   while (first < canon.size()) {
     if (done[first]) { ++first; continue; }
     Draft d;
-    uint64_t blocked = 0;
+    uint64_t blocked = 0, solo_mask = 0;
     std::vector<unsigned> bits;
     size_t scanned_blocked = 0;
     for (size_t i = first; i < canon.size(); ++i) {
@@ -582,6 +592,14 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       uint64_t mask = 0;
       for (unsigned p : canon[i].pos) mask |= uint64_t(1) << p;
       bool take = !(mask & blocked) && int(d.ids.size()) < max_per_pass;
+      if (take && !d.ids.empty()) {
+        if (d.solo) take = !(mask & ~solo_mask) && !canon[i].dr1;
+        else if (is_solo(canon[i])) take = false;
+      }
+      if (take && d.ids.empty() && is_solo(canon[i])) {
+        d.solo = true;
+        solo_mask = mask;
+      }
       if (take) {
         std::vector<unsigned> u = bits;
         for (unsigned p : canon[i].pos)
@@ -623,8 +641,20 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
   size_t mat_bytes = 0;
   const size_t esz = dtype == HQ_DTYPE_C64 ? 8 : 16;
   for (size_t d = 0; d < drafts.size(); ++d) {
-    merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost, dtype, mma_on, mma_min_k);
-    if (merge_pass_cost < 0 && merge_max_k > 2) {
+    if (drafts[d].solo) {
+      // everything in a solo pass acts inside the big gate's qubits: one matrix, in application order
+      Cluster c;
+      c.gate = canon[drafts[d].ids[0]];
+      for (unsigned p : c.gate.pos) c.mask |= uint64_t(1) << p;
+      c.ids.push_back(drafts[d].ids[0]);
+      for (size_t j = 1; j < drafts[d].ids.size(); ++j) {
+        merge_into(c.gate, canon[drafts[d].ids[j]]);
+        c.ids.push_back(drafts[d].ids[j]);
+      }
+      merged[d].push_back(std::move(c));
+    } else
+      merged[d] = merge_pass(canon, drafts[d].ids, merge_max_k, merge_pass_cost, dtype, mma_on, mma_min_k);
+    if (!drafts[d].solo && merge_pass_cost < 0 && merge_max_k > 2) {
       // second look at every cluster that grew beyond k = 2 on the strength of the slack: keep it only if it
       // really is cheaper than the same gates merged no further than k = 2 (a chain of two k = 2 gates is not, a
       // triangle of three is)

@@ -578,3 +578,39 @@ def test_tcgen05_norm_and_error_over_many_gates(hb):
     finally:
         hb.lib.hq_set_umma(old)
     assert abs(drift) < 3.0 * abs(drift_mma_sync) + 1e-6, (drift, drift_mma_sync)
+
+
+def test_big_gates_inside_a_circuit_run_as_solo_tcgen05_passes(hb, oracle, c_oracle):
+    """A complex64 circuit of 1-/2-qubit gates with dense 4-, 5- and 6-qubit gates in between: the planner gives each
+    big gate a pass of its own (tcgen05 kernel), multiplies the gates acting inside its qubits into it, and fuses the
+    rest around it; result against the oracle, and against the complex128 plan (all tile passes)."""
+    rng = np.random.default_rng(2024)
+    n = 16
+    gates = []
+    big = 0
+    for layer in range(12):
+        for _ in range(6):
+            k = int(rng.integers(1, 3))
+            gates.append((_haar(rng, k), [int(x) for x in rng.permutation(n)[:k]]))
+        if layer % 2 == 0:
+            k = 4 + (layer // 2) % 3
+            pos = [int(x) for x in rng.permutation(n)[:k]]
+            gates.append((_haar(rng, k), pos))
+            gates.append((_haar(rng, 2), pos[1:3]))              # acts inside the big gate: absorbed
+            big += 1
+    psi = _rand_state(rng, n, "complex64")
+    ref = oracle.evolve_oracle(psi, [(U.astype("complex64"), p) for U, p in gates], c_oracle)
+    plan = hb.Plan(gates, n, "complex64")
+    assert plan.n_umma_passes == big == 6
+    assert plan.n_passes < len(gates) // 3                        # the small gates are still fused
+    before = hb.lib.hq_umma_launch_count()
+    st = hb.DeviceState(n, "complex64").upload(psi)
+    plan.run(st)
+    out = st.download()
+    assert hb.lib.hq_umma_launch_count() == before + big
+    assert np.abs(out - ref).max() <= TOL["complex64"]
+    st128 = hb.DeviceState(n, "complex128").upload(psi.astype("complex128"))
+    p128 = hb.Plan(gates, n, "complex128")
+    assert p128.n_umma_passes == 0
+    p128.run(st128)
+    assert np.abs(st128.download() - out).max() <= TOL["complex64"]

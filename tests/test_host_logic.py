@@ -109,6 +109,25 @@ def test_merging_follows_the_measured_cost_table():
         assert mats([[1, 2, 3], [2, 3, 4]]) == 1                # two k = 3 sharing two bits -> k = 4
 
 
+def test_big_complex64_gates_get_a_pass_of_their_own():
+    """A dense complex64 gate of 4..6 qubits opens a "solo" pass (one launch of the tcgen05 kernel on the GPU): only
+    gates acting inside its qubits join, and they are multiplied into its matrix; everything else is fused around
+    it as usual.  complex128 (no tcgen05 path) keeps fusing such gates into tile passes."""
+    from helpers import Emu
+    emu = Emu()
+    n = 14
+    gates = [[0, 1], [5, 9], [1, 4, 7, 9, 12], [4, 12], [7], [2, 3], [9, 13], [0, 1, 2, 3]]
+    passes = emu.plan(0, n, gates, None)
+    by_gate = {g: i for i, p in enumerate(passes) for g in p["gate_ids"]}
+    assert sorted(by_gate) == list(range(len(gates)))
+    solo5, solo4 = passes[by_gate[2]], passes[by_gate[7]]
+    assert sorted(solo5["gate_ids"]) == [2, 3, 4] and solo5["n_kernel_gates"] == 1      # absorbed [4, 12] and [7]
+    assert solo4["gate_ids"] == [7] and solo4["n_kernel_gates"] == 1
+    assert by_gate[0] < by_gate[2] < by_gate[6] < by_gate[7]                             # order of overlapping gates kept
+    assert len(emu.plan(1, n, gates, None)) == 1                                         # complex128: one fused pass
+    assert len(emu.plan(0, 11, [[0, 1], [1, 4, 7, 9, 10]], None)) == 1                   # fewer than k + 7 qubits: fused
+
+
 def test_plan_sharded_rejects_gates_wider_than_a_shard():
     """plan_sharded() used to loop forever when a gate touched more qubits than a rank holds."""
     import numpy as np
