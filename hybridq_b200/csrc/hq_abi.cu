@@ -585,6 +585,25 @@ int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len) {
   return 0;
 }
 
+/* scalar + rank-one gates of the plan that run in the sparse form (scalar folded into another matrix, only the
+ * amplitudes with a non-zero u / v component touched), e.g. depolarizing channels of a density-matrix circuit */
+int hq_plan_sparse_rank_one_gates(const hq_plan* plan) {
+  if (!plan) return -1;
+  const size_t esz = plan->plan.dtype == HQ_DTYPE_C64 ? 4 : 8;
+  int cnt = 0;
+  for (const hq::PassInfo& pi : plan->plan.passes)
+    for (uint32_t g = 0; g < pi.header.n_gates; ++g) {
+      HqGateDesc gd;
+      memcpy(&gd, plan->plan.program.data() + pi.header.gates_off + size_t(g) * sizeof(HqGateDesc), sizeof(gd));
+      if (gd.kind != HQ_GATE_DR1) continue;
+      const unsigned char* flag = plan->plan.program.data() + gd.mat_off + esz * (2 + (size_t(4) << gd.k) + 1);   // trailer[0].im
+      double f = 0;
+      if (esz == 4) { float x; memcpy(&x, flag, 4); f = x; } else memcpy(&f, flag, 8);
+      cnt += f != 0 ? 1 : 0;
+    }
+  return cnt;
+}
+
 int hq_plan_pass_info(const hq_plan* plan, int pass, unsigned int* out, int out_len) {
   if (!plan || pass < 0 || pass >= int(plan->plan.passes.size())) return fail("bad pass index", 1);
   const HqPassHeader& ph = plan->plan.passes[size_t(pass)].header;

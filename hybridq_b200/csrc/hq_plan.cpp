@@ -56,6 +56,9 @@ struct Canon {               // gate with ascending positions and accordingly pe
   bool dr1 = false;
   std::complex<double> lambda;
   std::vector<std::complex<double>> u, v;
+  // sparse form (fold_dr1_scalars): lambda moved into another matrix of the plan (u already divided by it), the gate
+  // is 1 + u v^T and touches only the amplitudes where u or v is non-zero
+  bool dr1_folded = false;
 };
 
 // Is U = lambda * 1 + u v^T?  u and v are read off the row and the column of the largest OFF-diagonal entry
@@ -422,7 +425,7 @@ std::vector<std::complex<double>> embed(const Canon& c, const std::vector<unsign
 }
 
 template <typename T>
-void write_dr1(std::vector<unsigned char>& prog, size_t off, const Canon& c) {
+void write_dr1(std::vector<unsigned char>& prog, size_t off, const Canon& c, const uint16_t* tbl_x) {
   T* out = reinterpret_cast<T*>(prog.data() + off);
   const size_t dim = size_t(1) << c.k;
   out[0] = T(c.lambda.real());
@@ -433,6 +436,38 @@ void write_dr1(std::vector<unsigned char>& prog, size_t off, const Canon& c) {
     out[2 + 2 * dim + 2 * i] = T(c.v[i].real());
     out[2 + 2 * dim + 2 * i + 1] = T(c.v[i].imag());
   }
+  // trailer of the sparse form (gate_dr1 in hq_tile.cuh): [0] = (number of listed units, folded flag), then per listed
+  // unit s < 4 five complex slots: (slot offset of the unit = tbl_x[m], 0), v of its first amplitude, v of its second
+  // (complex64 with a target on amplitude bit 0: a unit holds two amplitudes of the group), u likewise.  Unused
+  // entries repeat unit 0 with zero u and v.
+  T* tr = out + 2 + 4 * dim;
+  for (int i = 0; i < 2 * (1 + 5 * 4); ++i) tr[i] = T(0);
+  const bool pairs = sizeof(T) == 4 && c.pos[0] == 0;
+  const size_t per = pairs ? 2 : 1, units = dim / per;
+  std::vector<size_t> listed;
+  for (size_t m = 0; m < units; ++m) {
+    bool nzu = false;
+    for (size_t e = 0; e < per; ++e)
+      nzu = nzu || c.u[m * per + e] != std::complex<double>(0, 0) || c.v[m * per + e] != std::complex<double>(0, 0);
+    if (nzu) listed.push_back(m);
+  }
+  const bool sparse = c.dr1_folded && !listed.empty() && listed.size() <= 4;
+  tr[0] = T(listed.size());
+  tr[1] = T(sparse ? 1 : 0);
+  if (sparse)
+    for (size_t s4 = 0; s4 < 4; ++s4) {
+      const bool real = s4 < listed.size();
+      const size_t m = real ? listed[s4] : listed[0];
+      T* e = tr + 2 * (1 + 5 * s4);
+      e[0] = T(tbl_x[m]);
+      if (!real) continue;
+      for (size_t a = 0; a < per; ++a) {
+        e[2 + 2 * a] = T(c.v[m * per + a].real());
+        e[3 + 2 * a] = T(c.v[m * per + a].imag());
+        e[6 + 2 * a] = T(c.u[m * per + a].real());
+        e[7 + 2 * a] = T(c.u[m * per + a].imag());
+      }
+    }
 }
 
 // first := second * first on the union of their positions (second is applied after first).
@@ -673,6 +708,41 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       }
       merged[d].swap(refined);
     }
+  }
+  // ---- sparse "scalar + rank one" gates (a depolarizing channel as a super-operator: u = v = the vectorised identity,
+  // 4 of 16 entries): lambda * 1 + u v^T = lambda * (1 + (u / lambda) v^T), and a scalar commutes with everything, so
+  // the product of all such lambdas goes into ONE dense matrix of the plan and each gate only touches the amplitudes
+  // where u or v is non-zero (gate_dr1 sparse form).  Needs a dense matrix somewhere in the plan to carry the scalar.
+  {
+    Canon* carrier = nullptr;
+    for (size_t d = 0; d < drafts.size() && !carrier; ++d)
+      for (Cluster& c : merged[d])
+        if (!c.gate.dr1) { carrier = &c.gate; break; }
+    std::complex<double> total(1, 0);
+    if (carrier)
+      for (size_t d = 0; d < drafts.size(); ++d)
+        for (Cluster& c : merged[d]) {
+          Canon& g = c.gate;
+          if (!g.dr1) continue;
+          double umax = 0, vmax = 0;
+          for (const auto& x : g.u) umax = std::max(umax, std::abs(x));
+          for (const auto& x : g.v) vmax = std::max(vmax, std::abs(x));
+          size_t nz = 0;
+          for (size_t i = 0; i < g.u.size(); ++i) {
+            if (std::abs(g.u[i]) <= 1e-14 * umax) g.u[i] = 0;
+            if (std::abs(g.v[i]) <= 1e-14 * vmax) g.v[i] = 0;
+            if (g.u[i] != std::complex<double>(0, 0) || g.v[i] != std::complex<double>(0, 0)) ++nz;
+          }
+          if (2 * nz > g.u.size() || std::abs(g.lambda) < 1e-3) continue;
+          for (auto& x : g.u) x /= g.lambda;
+          total *= g.lambda;
+          g.lambda = 1;
+          g.dr1_folded = true;
+        }
+    if (carrier && total != std::complex<double>(1, 0))
+      for (auto& x : carrier->U) x *= total;
+  }
+  for (size_t d = 0; d < drafts.size(); ++d) {
     total_gates += merged[d].size();
     // single gates may use shorter runs than the fuser is allowed to create
     const int L = choose_run_bits(drafts[d].bits, T, drafts[d].ids.size() > 1 ? fuse_min_run : hard_min_run);
@@ -695,7 +765,7 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       gl.dr1 = c.dr1 && !lone_small;
       gl.mma = !gl.dr1 && mma_on && !lone_small && int(c.k) >= mma_min_k && int(c.k) <= HQ_MMA_MAX_K &&
                mma_layout(gl.tpos, int(c.k), Tbits, V, gl.L);
-      gl.bytes = gl.dr1 ? (((esz * (1 + (size_t(2) << c.k))) + 15) & ~size_t(15))
+      gl.bytes = gl.dr1 ? (((esz * (1 + (size_t(2) << c.k) + 21)) + 15) & ~size_t(15))
                         : (gl.mma ? mma_frag_bytes(c.k) : (((esz << (2 * c.k)) + 15) & ~size_t(15)));
       mat_bytes += gl.bytes;
     }
@@ -814,8 +884,8 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
       }
       memcpy(plan.program.data() + gate_cursor * sizeof(HqGateDesc), &gd, sizeof(gd));
       if (gd.kind == HQ_GATE_DR1) {
-        if (dtype == HQ_DTYPE_C64) write_dr1<float>(plan.program, mat_cursor, c);
-        else write_dr1<double>(plan.program, mat_cursor, c);
+        if (dtype == HQ_DTYPE_C64) write_dr1<float>(plan.program, mat_cursor, c, gd.tbl_x);
+        else write_dr1<double>(plan.program, mat_cursor, c, gd.tbl_x);
       } else if (gd.kind == HQ_GATE_MMA)
         write_mma_fragments(plan.program, mat_cursor, c, gl.L, dtype);
       else if (dtype == HQ_DTYPE_C64)

@@ -682,6 +682,55 @@ HQ_DEV void gate_dr1_f32(float4* tile, const HqGateDesc* __restrict__ g, const f
   const float2 lam = HQ_LDG(&p[0]);
   const float2* __restrict__ u = p + 1;
   const float2* __restrict__ v = p + 1 + DIM;
+  // sparse form (planner, "sparse scalar + rank one"): lambda has been moved into another matrix of the plan and at
+  // most four units of the group hold a non-zero u or v component; the trailer lists them compactly -- per unit its
+  // slot offset and its v and u components -- so that every load below is independent of the others (one latency)
+  // and the gate is 4 LDS + 4 STS per work item.  Nothing else of the group is touched.
+  const float2* __restrict__ sp = p + 1 + 2 * DIM;
+  if (HQ_LDG(&sp[0]).y != 0.f) {
+    uint32_t xm[4];
+    float2 va[4], vb[4], ua[4], ub[4];
+    HQ_UNROLL
+    for (int s = 0; s < 4; ++s) {
+      xm[s] = uint32_t(HQ_LDG(&sp[1 + 5 * s]).x);
+      va[s] = HQ_LDG(&sp[2 + 5 * s]);
+      ua[s] = HQ_LDG(&sp[4 + 5 * s]);
+      if (LOW) {
+        vb[s] = HQ_LDG(&sp[3 + 5 * s]);
+        ub[s] = HQ_LDG(&sp[5 + 5 * s]);
+      }
+    }
+    HQ_NOUNROLL
+    for (uint32_t it = 0; it < niter; ++it) {
+      const uint32_t sb = st ^ iter_offset(ib, it);
+      float4 x[4];
+      HQ_UNROLL
+      for (int s = 0; s < 4; ++s) x[s] = tile[sb ^ xm[s]];
+      float d0r = 0.f, d0i = 0.f, d1r = 0.f, d1i = 0.f;
+      HQ_UNROLL
+      for (int s = 0; s < 4; ++s) {
+        if (!LOW) {
+          cmac(d0r, d0i, va[s].x, va[s].y, x[s].x, x[s].y);
+          cmac(d1r, d1i, va[s].x, va[s].y, x[s].z, x[s].w);
+        } else {
+          cmac(d0r, d0i, va[s].x, va[s].y, x[s].x, x[s].y);
+          cmac(d0r, d0i, vb[s].x, vb[s].y, x[s].z, x[s].w);
+        }
+      }
+      HQ_UNROLL
+      for (int s = 0; s < 4; ++s) {
+        if (!LOW) {
+          cmac(x[s].x, x[s].y, ua[s].x, ua[s].y, d0r, d0i);
+          cmac(x[s].z, x[s].w, ua[s].x, ua[s].y, d1r, d1i);
+        } else {
+          cmac(x[s].x, x[s].y, ua[s].x, ua[s].y, d0r, d0i);
+          cmac(x[s].z, x[s].w, ub[s].x, ub[s].y, d0r, d0i);
+        }
+        tile[sb ^ xm[s]] = x[s];
+      }
+    }
+    return;
+  }
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
     const uint32_t sb = st ^ iter_offset(ib, it);
@@ -732,6 +781,33 @@ HQ_DEV void gate_dr1_f64(double2* tile, const HqGateDesc* __restrict__ g, const 
   const double2 lam = HQ_LDG(&p[0]);
   const double2* __restrict__ u = p + 1;
   const double2* __restrict__ v = p + 1 + DIM;
+  const double2* __restrict__ sp = p + 1 + 2 * DIM;           // sparse form, see gate_dr1_f32
+  if (HQ_LDG(&sp[0]).y != 0.) {
+    uint32_t xm[4];
+    double2 va[4], ua[4];
+    HQ_UNROLL
+    for (int s = 0; s < 4; ++s) {
+      xm[s] = uint32_t(HQ_LDG(&sp[1 + 5 * s]).x);
+      va[s] = HQ_LDG(&sp[2 + 5 * s]);
+      ua[s] = HQ_LDG(&sp[4 + 5 * s]);
+    }
+    HQ_NOUNROLL
+    for (uint32_t it = 0; it < niter; ++it) {
+      const uint32_t sb = st ^ iter_offset(ib, it);
+      double2 x[4];
+      HQ_UNROLL
+      for (int s = 0; s < 4; ++s) x[s] = tile[sb ^ xm[s]];
+      double dr = 0., di = 0.;
+      HQ_UNROLL
+      for (int s = 0; s < 4; ++s) cmac(dr, di, va[s].x, va[s].y, x[s].x, x[s].y);
+      HQ_UNROLL
+      for (int s = 0; s < 4; ++s) {
+        cmac(x[s].x, x[s].y, ua[s].x, ua[s].y, dr, di);
+        tile[sb ^ xm[s]] = x[s];
+      }
+    }
+    return;
+  }
   HQ_NOUNROLL
   for (uint32_t it = 0; it < niter; ++it) {
     const uint32_t sb = st ^ iter_offset(ib, it);

@@ -86,6 +86,8 @@ class Plan:
         self.n_passes = lib.hq_plan_num_passes(self._h)
         # passes (one dense complex64 k = 4 .. 6 matrix) that run on the tcgen05 / TMEM kernel (hq_umma.cuh)
         self.n_umma_passes = lib.hq_plan_umma_passes(self._h)
+        # scalar + rank-one gates (depolarizing channels) that run in the sparse form (hq_plan.cpp, fold of the scalars)
+        self.n_sparse_rank_one = lib.hq_plan_sparse_rank_one_gates(self._h)
 
     def __del__(self):
         h = getattr(self, "_h", None)

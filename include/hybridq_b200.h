@@ -186,6 +186,11 @@ int hq_plan_run_range(hq_plan* plan, void* state, int first, int last, void* str
  * slot, 1 tensor cores (mma.sync 3xTF32 / FP64), 2 generic FMA path (incl. the direct kernel), 3 two-phase path,
  * 4 scalar + rank-one form (a depolarizing channel's super-operator: lambda * 1 + u v^T); out has 40 entries */
 int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len);
+/* how many of the scalar + rank-one gates run in the sparse form: lambda * 1 + u v^T = lambda * (1 + (u / lambda) v^T),
+ * the scalars of all such gates multiplied into one dense matrix of the plan, and each gate touching only the
+ * amplitudes where u or v is non-zero (a 2-qubit depolarizing channel as a 4-qubit super-operator: 4 of 16,
+ * hybridq/noise/channel/channel.py:413-529) */
+int hq_plan_sparse_rank_one_gates(const hq_plan* plan);
 
 /* ---- multi-GPU: rank-bit <-> local-bit exchange fused into a pass (no reference counterpart: the reference's
  * evolution path refuses MPI, hybridq/circuit/simulation/simulation.py:379-380) ----

@@ -147,6 +147,10 @@ def test_scalar_plus_rank_one_gates(emu, oracle, c_oracle):
                 assert np.abs(out - ref).max() < tol, (ctype, k, pos)
                 plan = hb.Plan(gates, n, ctype)
                 assert plan.arithmetic()[f"k{k}"].get("scalar_plus_rank_one") == 1, plan.arithmetic()
+                # the channel (u = v = vectorised identity: 4 of 16 entries) runs in the sparse form, its scalar
+                # carried by one of the dense gates; a dense u v^T does not
+                assert plan.n_sparse_rank_one == (1 if U is depol2 else 0)
+            assert hb.Plan([(U, [0, 3, 5, 9][:k])], n, ctype).n_sparse_rank_one == 0       # nothing to carry the scalar
     # a dense Haar matrix is not of that form
     from hybridq_b200.circuits import haar_unitary
     assert "scalar_plus_rank_one" not in str(hb.Plan([(haar_unitary(16, rng), [1, 3, 5, 7]), (other, [2, 9])], n, "complex64").arithmetic())
