@@ -577,7 +577,7 @@ int hq_plan_arith_counts(const hq_plan* plan, unsigned int* out, int out_len) {
       HqGateDesc gd;
       memcpy(&gd, plan->plan.program.data() + pi.header.gates_off + size_t(g) * sizeof(HqGateDesc), sizeof(gd));
       if (gd.k < 1 || gd.k > 8) continue;
-      const bool fast = plan->plan.dtype == HQ_DTYPE_C64 && pi.header.max_k <= 3 && g < HQ_FAST_SLOTS &&
+      const bool fast = plan->plan.dtype == HQ_DTYPE_C64 && pi.header.max_k <= 3 && g < 32u &&
                         ((pi.header.fast_mask >> g) & 1u) && pi.header.n_gates > 1;
       const unsigned a = fast ? 0u : (gd.kind == HQ_GATE_MMA ? 1u : (gd.kind == HQ_GATE_BIG ? 3u : (gd.kind == HQ_GATE_DR1 ? 4u : 2u)));
       ++out[5 * (gd.k - 1) + a];

@@ -199,8 +199,9 @@ void emu_pass(typename hq::Traits<T>::Unit* state, unsigned n, const unsigned ch
     }
     for (uint32_t gi = 0; gi < ph.n_gates; ++gi) {
       const HqGateDesc* g = gates + gi;
-      if (V == 1 && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
-        for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), int(gi), g, ph, Tu, tid);
+      if (V == 1 && gi < 32u && ((ph.fast_mask >> gi) & 1u)) {
+        const int slot = __builtin_popcount(ph.fast_mask & ((1u << gi) - 1u));
+        for (int tid = 0; tid < HQ_THREADS; ++tid) emu_fast_slot(tile.data(), slot, g, ph, Tu, tid);
       } else if (g->kind == HQ_GATE_DR1) {
         for (int tid = 0; tid < HQ_THREADS; ++tid) hq::gate_dr1_dispatch(tile.data(), g, g->k, prog, g->mat_off, Tu, tid);
       } else if (g->kind == HQ_GATE_MMA) {

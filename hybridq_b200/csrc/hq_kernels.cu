@@ -268,15 +268,17 @@ __device__ __forceinline__ void apply_pass_gates(typename Traits<T>::Unit* tile,
   if (any_fast && (ph.fast_mask & 1u)) sr = load_stream_regs(gates, tid);
   for (uint32_t gi = 0; gi < n_gates; ++gi) {
     const HqGateDesc* g = gates + gi;
-    if (any_fast && gi < HQ_FAST_SLOTS && ((ph.fast_mask >> gi) & 1u)) {
-      gate_fast_slot<MAXK>(tile, sr, ph, gi, Tu, tid);       // complex64 k <= 3: constant-bank FFMA2
+    if (any_fast && gi < 32u && ((ph.fast_mask >> gi) & 1u)) {
+      // complex64 k <= 3: constant-bank FFMA2; slot = how many slot matrices came before (other kinds in between --
+      // e.g. the channels of a density-matrix pass -- do not use up slots)
+      gate_fast_slot<MAXK>(tile, sr, ph, uint32_t(__popc(ph.fast_mask & ((1u << gi) - 1u))), Tu, tid);
       // the next slot gate's addressing constants travel while this thread waits at the barrier
-      if (gi + 1 < n_gates && gi + 1 < HQ_FAST_SLOTS && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
+      if (gi + 1 < n_gates && gi + 1 < 32u && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
       if ((ph.chain_mask >> gi) & 1u) __syncwarp();      // the next gate's warps work on the very same units
       else sync();
       continue;
     }
-    if (any_fast && gi + 1 < n_gates && gi + 1 < HQ_FAST_SLOTS && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
+    if (any_fast && gi + 1 < n_gates && gi + 1 < 32u && ((ph.fast_mask >> (gi + 1)) & 1u)) sr = load_stream_regs(g + 1, tid);
     const uint32_t k = __ldg(&g->k);
     const uint32_t mat_off = __ldg(&g->mat_off);
     const uint32_t kind = __ldg(&g->kind);

@@ -894,13 +894,15 @@ int plan_build(Plan& plan, int dtype, unsigned n, const std::vector<GateIn>& gat
         write_matrix<double>(plan.program, mat_cursor, c, gd.kind == HQ_GATE_BIG);
       mat_cursor += gl.bytes;
       ++gate_cursor;
-      if (dtype == HQ_DTYPE_C64 && gd.kind == HQ_GATE_SMALL && opts.fast_slots != 0 && ci < HQ_FAST_SLOTS &&
+      // slot s = the s-th eligible matrix of the pass (bit ci of fast_mask marks it; the kernel counts the bits below)
+      const unsigned slots_used = unsigned(__builtin_popcount(pi.header.fast_mask));
+      if (dtype == HQ_DTYPE_C64 && gd.kind == HQ_GATE_SMALL && opts.fast_slots != 0 && ci < 32 && slots_used < HQ_FAST_SLOTS &&
           c.k <= HQ_FAST_MAX_K && Tbits - int(c.k) >= 1) {
         pi.header.fast_mask |= 1u << ci;
-        pi.header.fast_k[ci] = uint8_t(c.k | (gd.tpos[0] == 0 ? 4u : 0u));
+        pi.header.fast_k[slots_used] = uint8_t(c.k | (gd.tpos[0] == 0 ? 4u : 0u));
         for (size_t e = 0; e < (size_t(1) << (2 * c.k)); ++e) {
-          pi.header.fast_u[ci][2 * e] = float(c.U[e].real());
-          pi.header.fast_u[ci][2 * e + 1] = float(c.U[e].imag());
+          pi.header.fast_u[slots_used][2 * e] = float(c.U[e].real());
+          pi.header.fast_u[slots_used][2 * e + 1] = float(c.U[e].imag());
         }
       }
       for (unsigned id : cluster.ids) pi.gate_ids.push_back(canon_id[id]);
