@@ -124,6 +124,7 @@ _proto("hq_ipc_close", ctypes.c_int, _vp)
 _proto("hq_set_ring", ctypes.c_int, ctypes.c_int)
 _proto("hq_set_umma", ctypes.c_int, ctypes.c_int)
 _proto("hq_umma_launch_count", ctypes.c_uint64)
+_proto("hq_direct_launch_count", ctypes.c_uint64)
 _proto("hq_plan_umma_passes", ctypes.c_int, _vp)
 _proto("hq_plan_sparse_rank_one_gates", ctypes.c_int, _vp)
 _proto("hq_set_tuning", ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int)
@@ -140,7 +141,7 @@ EXPORTED = [
     "hq_scale_dev", "hq_marginal_dev", "hq_project_dev", "hq_marginal_cond_dev", "hq_project_mask_dev", "hq_plan_create", "hq_plan_create_bitperm", "hq_plan_destroy", "hq_plan_num_passes",
     "hq_plan_num_gates", "hq_plan_num_kernel_gates", "hq_plan_flops", "hq_plan_arith_counts", "hq_plan_pass_info", "hq_plan_pass_gates", "hq_plan_run", "hq_plan_run_range",
     "hq_plan_run_range_xchg", "hq_plan_run_io", "hq_host_is_pinned", "hq_ipc_get_handle", "hq_ipc_open", "hq_ipc_close", "hq_set_ring",
-    "hq_set_umma", "hq_umma_launch_count", "hq_plan_umma_passes", "hq_plan_sparse_rank_one_gates",
+    "hq_set_umma", "hq_umma_launch_count", "hq_direct_launch_count", "hq_plan_umma_passes", "hq_plan_sparse_rank_one_gates",
     "hq_set_tuning", "hq_launch_count", "hq_launch_count_reset",
 ]
 

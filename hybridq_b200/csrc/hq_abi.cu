@@ -80,6 +80,7 @@ void fill_gate(hq::GateIn& g, const T* U, const unsigned* pos, unsigned k) {
 
 int g_use_umma = 1;     // complex64 passes made of one dense k = 4 .. 6 matrix go to the tcgen05 kernel (hq_umma.cuh)
 std::atomic<uint64_t> g_umma_launches{0};
+std::atomic<uint64_t> g_direct_launches{0};
 int g_use_direct = 1;   // single k <= 2 gate passes go to the shared-memory-free kernel
 
 // xchg (may be null): exchange redirect applied to the write-back of the LAST pass of the range
@@ -110,8 +111,10 @@ int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, in
     HqGateDesc gd;
     if (ph.n_gates == 1) memcpy(&gd, plan.program.data() + ph.gates_off, sizeof(gd));
     // (the gate's own k and kind decide, not the header's kernel class: a lone scalar + rank-one k = 4 gate carries
-    // max_k = 3 -- found by tools/sanitize_target.py in round 2)
-    if (g_use_direct && !xg && ph.n_gates == 1 && !ph.has_perm && gd.kind == HQ_GATE_SMALL && gd.k <= 3 &&
+    // max_k = 3 -- found by tools/sanitize_target.py in round 2; SMALL and ROWPAIR -- the complex128 k = 2, 3 register
+    // scheme -- both keep the plain row-major matrix the direct kernel reads)
+    if (g_use_direct && !xg && ph.n_gates == 1 && !ph.has_perm && (gd.kind == HQ_GATE_SMALL || gd.kind == HQ_GATE_ROWPAIR) &&
+        gd.k <= 3 &&
         plan.n_qubits >= gd.k + 1) {
       // measured (profiles/): the direct kernel runs a lone 1-/2-/3-qubit gate at copy bandwidth
       const unsigned L = ph.tile_bits - ph.n_high;
@@ -121,6 +124,7 @@ int run_plan_passes(hq::Plan& plan, const unsigned char* d_prog, void* state, in
                                             gd.k, stream);
       if (rc) return cuda_fail("direct gate launch", rc);
       ++g_launches;
+      ++g_direct_launches;
       continue;
     }
     if (g_use_umma && !xg && plan.passes[size_t(p)].umma_off && ph.n_gates == 1 && d_prog) {
@@ -760,6 +764,7 @@ int hq_set_umma(int mode) {
   return old;
 }
 uint64_t hq_umma_launch_count(void) { return g_umma_launches.load(); }
+uint64_t hq_direct_launch_count(void) { return g_direct_launches.load(); }
 int hq_plan_umma_passes(const hq_plan* plan) {
   if (!plan) return -1;
   int cnt = 0;

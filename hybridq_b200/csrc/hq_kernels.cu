@@ -194,13 +194,21 @@ __device__ __forceinline__ void rowpair_dispatch(float4*, const HqGateDesc*, uin
 // One out-of-line copy per kernel of everything but the two-phase path: the register paths, the
 // complex128 row-pair scheme and the tensor-core path (it is called from the unrolled fast-slot
 // sequence as well as from the gate loop).
+// (a function of its own: its register needs -- the compact sparse form keeps four units and their constants live --
+// must not weigh on the allocation of the tensor-core and register paths below)
+template <typename Unit>
+__device__ __noinline__ void gate_dr1_outofline(Unit* tile, const HqGateDesc* g, uint32_t k, const unsigned char* prog,
+                                                uint32_t mat_off, int Tu, int tid) {
+  gate_dr1_dispatch(tile, g, k, prog, mat_off, Tu, tid);
+}
+
 template <int MAXK, int MMAK, typename Unit>
 __device__ __noinline__ void gate_small_generic(Unit* tile, const HqGateDesc* g, uint32_t k, uint32_t kind,
                                                 const unsigned char* prog, uint32_t mat_off, int Tu, int tid) {
   if (kind == HQ_GATE_MMA) {
     gate_mma_dispatch<MMAK>(tile, g, k, prog, tid);
   } else if (kind == HQ_GATE_DR1) {
-    if (MAXK >= 3) gate_dr1_dispatch(tile, g, k, prog, mat_off, Tu, tid);     // scalar + rank one (k = 3, 4)
+    if (MAXK >= 3) gate_dr1_outofline(tile, g, k, prog, mat_off, Tu, tid);     // scalar + rank one (k = 3, 4)
   } else if (IsF64Unit<Unit>::value && kind == HQ_GATE_ROWPAIR) {
     rowpair_dispatch<MAXK>(tile, g, k, prog, mat_off, Tu, tid);
   } else {

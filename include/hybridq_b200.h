@@ -233,6 +233,8 @@ int hq_set_ring(int mode);
  * hq_umma_launch_count: launches of that kernel by this process.  hq_plan_umma_passes: passes of a plan that qualify. */
 int hq_set_umma(int mode);
 uint64_t hq_umma_launch_count(void);
+/* launches of the shared-memory-free direct kernel (a pass made of one gate with k <= 3, either precision) from plans */
+uint64_t hq_direct_launch_count(void);
 int hq_plan_umma_passes(const hq_plan* plan);
 
 /* counters: kernels launched by this library in this process since the last reset */

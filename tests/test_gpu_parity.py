@@ -614,3 +614,21 @@ def test_big_gates_inside_a_circuit_run_as_solo_tcgen05_passes(hb, oracle, c_ora
     assert p128.n_umma_passes == 0
     p128.run(st128)
     assert np.abs(st128.download() - out).max() <= TOL["complex64"]
+
+
+@pytest.mark.parametrize("ctype", ["complex64", "complex128"])
+def test_lone_small_gates_take_the_direct_kernel(hb, oracle, c_oracle, ctype):
+    """A pass made of one gate with k <= 3 runs on the shared-memory-free direct kernel at copy bandwidth, in both
+    precisions (regression: complex128 k = 2, 3 gates carry the row-pair kind and were sent to the tile kernel --
+    config 3's lone k = 3 row dropped from 20.5 to 7.9 gate-applies/s before this was caught)."""
+    rng = np.random.default_rng(41)
+    n = 14
+    for k, pos in ((1, [6]), (2, [0, 9]), (2, [3, 12]), (3, [1, 7, 13]), (3, [0, 4, 8])):
+        U = _haar(rng, k)
+        psi = _rand_state(rng, n, ctype)
+        ref = oracle.evolve_oracle(psi, [(U.astype(ctype), pos)], c_oracle)
+        before = hb.lib.hq_direct_launch_count()
+        st = hb.DeviceState(n, ctype).upload(psi)
+        hb.Plan([(U, pos)], n, ctype).run(st)
+        assert hb.lib.hq_direct_launch_count() == before + 1, (ctype, k, pos)
+        assert np.abs(st.download() - ref).max() <= TOL[ctype]
