@@ -350,6 +350,10 @@ def simulate(circuit,
 
     info = {"runtime (s)": runtime, "pre-pass (s)": t_pre, "plan (s)": t_plan, "upload (s)": t_up,
             "n_gate_applies": n_gate_applies, "n_passes": n_passes, "n_qubits": n_qubits,
+            # passes on the tcgen05 / TMEM kernel (one dense complex64 4..6-qubit matrix each) and channels that run
+            # in the sparse scalar + rank-one form
+            "n_tcgen05_passes": sum(p.n_umma_passes for kind, p in plans if kind == "gates"),
+            "n_sparse_channels": sum(p.n_sparse_rank_one for kind, p in plans if kind == "gates"),
             "transfers folded into passes": {"upload": io_src is not None, "download": io_dst is not None}}
     if kwargs["return_numpy_array"]:
         t_down = time.perf_counter()
