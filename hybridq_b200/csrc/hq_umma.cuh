@@ -144,6 +144,26 @@ __host__ __device__ constexpr int umma_ksplit() {
   return KQ == 6 ? 2 : 1;
 }
 
+// ---- the MODEB lane map, shared by the kernel and by the host-side exhaustive check (tools/umma_lane_map_check.cu) ----
+// lane -> its share of the K-chunk number and of the row number: lane bit b counts chunks if bit b of cmask is set
+__host__ __device__ inline void umma_lane_split(unsigned cmask, int lane, int& c_lane, int& r_lane) {
+  int ci = 0, ri = 0;
+  c_lane = 0;
+  r_lane = 0;
+  for (int b = 0; b < 5; ++b) {
+    if ((cmask >> b) & 1u) c_lane |= ((lane >> b) & 1) << ci++;
+    else r_lane |= ((lane >> b) & 1) << ri++;
+  }
+}
+// logical slot (chunk * 128 + row) of the unit a thread handles in iteration i of a sweep over nch chunks x 128 rows;
+// A = number of chunk bits among the lane bits.  q = warp * nch + i supplies the remaining 2 + A row bits, then the
+// remaining chunk bits.
+__host__ __device__ inline int umma_unit_slot(int warp, int i, int nch, int A, int c_lane, int r_lane) {
+  const int q = warp * nch + i;
+  const int r = ((q & ((4 << A) - 1)) << (5 - A)) | r_lane, c = ((q >> (2 + A)) << A) | c_lane;
+  return c * 128 + r;
+}
+
 // How a warp's lanes are spread over a tile's 16-byte units (row r, K-chunk c) while it is loaded and stored:
 //   MODEB = false: lane = 5 low row bits; thread r owns row r, iteration i handles K-chunk i.  Used when the five lowest
 //                  amplitude bits outside the lowest target are all non-targets (consecutive groups are contiguous).
@@ -235,19 +255,10 @@ __global__ void __launch_bounds__(128) hq_umma_gate_kernel(float2* __restrict__ 
   // q = warp * nch + i: row bits first (2 + A of them), then chunk bits
   const int A = MODEB ? int(p.nchunk) : 0;
   int c_lane = 0, r_lane = 0;
-  if (MODEB) {
-    int ci = 0, ri = 0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b) {
-      if ((p.cmask >> b) & 1) c_lane |= ((lane >> b) & 1) << ci++;
-      else r_lane |= ((lane >> b) & 1) << ri++;
-    }
-  }
+  if (MODEB) umma_lane_split(p.cmask, lane, c_lane, r_lane);
   auto unit_slot = [&](int i, int nch) {
     if (!MODEB) return i * 128 + tid;
-    const int q = warp * nch + i;
-    const int r = ((q & ((4 << A) - 1)) << (5 - A)) | r_lane, c = ((q >> (2 + A)) << A) | c_lane;
-    return c * 128 + r;
+    return umma_unit_slot(warp, i, nch, A, c_lane, r_lane);
   };
   // amplitude offset inside the tile of the unit in `slot`, K-chunks counted from chunk0
   auto unit_off = [&](int slot, int chunk0) { return rowoff[slot & 127] | dep[2 * (chunk0 + (slot >> 7))]; };

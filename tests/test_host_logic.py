@@ -141,3 +141,26 @@ def test_plan_sharded_rejects_gates_wider_than_a_shard():
         plan_sharded([(np.eye(2), [0])], n=2, g=2)
     ops, stats, where = plan_sharded([(np.eye(8), [0, 1, 4])], n=5, g=2)     # k = n - g: just fits
     assert stats["exchanges"] >= 1 and where == list(range(5))
+
+
+def test_tcgen05_lane_map_exhaustive(tmp_path):
+    """The memory-order lane map of the tcgen05 gate kernel (csrc/hq_umma.cuh) checked on the host for every target
+    set of 4..6 bits among the 12 lowest amplitude bits: bijection onto the tile, conflict-free shared-memory
+    quarter-warps with the skewed chunk stride, never more global lines than the row map
+    (tools/umma_lane_map_check.cu: only the __host__ __device__ helpers run, nvcc builds it without a GPU)."""
+    import json
+    import shutil
+    import subprocess
+    from helpers import ROOT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not shutil.which(nvcc):
+        import pytest
+        pytest.skip("nvcc not found")
+    exe = tmp_path / "umma_lane_map_check"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-o", str(exe),
+                    str(ROOT / "tools" / "umma_lane_map_check.cu")], check=True, capture_output=True, timeout=300)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["failures"] == 0 and res["target_sets"] >= 2200 and res["with_chunk_lanes"] > 1000
+    assert res["lines_per_quarter_memory_order_map"] < 0.6 * res["lines_per_quarter_rows_map"]
