@@ -1,20 +1,27 @@
-// hq_umma.cuh -- one dense k = 3 .. 5 gate on a complex64 state with the 5th-generation tensor cores:
+// hq_umma.cuh -- one dense k = 4, 5 or 6 gate on a complex64 state with the 5th-generation tensor cores:
 // `tcgen05.mma kind::tf32` issued by one thread per CTA, accumulators in TMEM, `tcgen05.ld` epilogue.
+// (The kernel template also instantiates for k = 3; the library uses it from k = 4, below that the FMA paths are exact
+// and as fast.)
 //
 // This is the "genuine dense contraction" case of the north star (replaces the runtime-k loop of
 // /root/reference/include/U.h:123-202): per group of 2^k amplitudes the gate is the real product (k = 5 shown)
 //     D[1 x 64] = A[1 x 64] * Bs^T,   A = the group's reals (re, im interleaved), Bs = real form of U,
 // and a CTA multiplies 128 groups at a time: M = 128, N = K = 64.  Accuracy: 3xTF32 -- hi * hi + lo * hi + hi * lo with
-// hi = the operand rounded to TF32 (nearest) and lo = the rounded remainder, all summed in the fp32 TMEM accumulator.
+// hi = the operand rounded to TF32 (nearest) and lo = the rounded remainder; the hi * hi products and the corrections
+// go to separate fp32 TMEM accumulators that the epilogue adds (see the kernel for why).
 //
 // Operand layout (K-major, no swizzle, validated bit-exact by tools/microbench_tcgen05.cu): 16-byte units,
-//     A unit (row r, K-chunk c)  at shared slot  c * 128 + r      (LBO = 128 units, SBO = 8 units)
-//     B unit (row n, K-chunk c)  at shared slot  c * N   + n      (LBO = N   units, SBO = 8 units)
+//     A unit (row r, K-chunk c)  at shared slot  c * LBO + r      (LBO = 128 units, or skewed, see below; SBO = 8)
+//     B unit (row n, K-chunk c)  at shared slot  c * N   + n      (LBO = N units, SBO = 8 units)
 // An A unit holds 4 consecutive reals = the two amplitudes 2c, 2c + 1 of the group, i.e. the pair that differs in
-// the gate's LOWEST target bit: thread r gathers them from global memory with 8-byte loads (for a fixed amplitude
-// number the 32 lanes of a warp read consecutive groups: contiguous when bit 0 is not a target), splits hi / lo in
-// registers and stores both copies with conflict-free 16-byte shared stores.  The epilogue reads row r of D back
-// from TMEM lane r and scatters the 32 output amplitudes with 8-byte stores.
+// the gate's LOWEST target bit.  In the plain mapping thread r gathers the units of row r from global memory (for a
+// fixed amplitude number the 32 lanes of a warp read consecutive groups: contiguous when the low bits are not
+// targets), splits hi / lo in registers and stores both copies with conflict-free 16-byte shared stores; the epilogue
+// reads row r of D back from TMEM lane r and scatters its output amplitudes.  With targets among the low bits the
+// lanes follow the memory order of the tile instead (MODEB, further down).
+//
+// Bring-up harness: tools/umma_gate_test.cu; host-side check of the lane map: tools/umma_lane_map_check.cu;
+// measurements: profiles/r02/umma_*, sweep_umma_n30.jsonl, ncu_umma_raw.csv; design notes: DESIGN.md section 3.
 #pragma once
 #include <cuda_runtime.h>
 
