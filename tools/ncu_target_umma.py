@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch sequence for `ncu --set full` on the tcgen05 lone-gate kernel (hq_umma.cuh), through the library:
 complex64 n = 28, one dense k = 5 gate and one dense k = 4 gate at spread-out targets, one k = 5 gate on the five lowest
-bits, then the same k = 5 gate on the mma.sync tile-kernel path it replaces.  Diagnostics only."""
+bits, one k = 6 gate, then the same k = 5 gate on the mma.sync tile-kernel path it replaces.  Diagnostics only."""
 import sys
 from pathlib import Path
 
@@ -19,7 +19,8 @@ torch.cuda.synchronize()
 rng = np.random.default_rng(3)
 plans = [hb.Plan([(haar_unitary(32, rng), [3, 7, 12, 20, 25])], n, ctype),
          hb.Plan([(haar_unitary(16, rng), [3, 7, 12, 20])], n, ctype),
-         hb.Plan([(haar_unitary(32, rng), [0, 1, 2, 3, 4])], n, ctype)]
+         hb.Plan([(haar_unitary(32, rng), [0, 1, 2, 3, 4])], n, ctype),
+         hb.Plan([(haar_unitary(64, rng), [3, 7, 12, 20, 25, 27])], n, ctype)]
 for rep in range(2):          # the first launch of each is the warm-up
     for p in plans:
         assert p.n_umma_passes == 1
