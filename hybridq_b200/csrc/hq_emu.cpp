@@ -429,4 +429,13 @@ int hq_emu_plan_dump(int dtype, unsigned n, unsigned n_gates, const unsigned* ks
   return w;
 }
 
+// the tcgen05 operand blocks of a 2^k x 2^k matrix (hq_plan.cpp umma_pack_matrix): U_flat = row-major (re, im) doubles,
+// hi / lo receive (2 * 2^k)^2 floats each
+void hq_emu_umma_pack(const double* U_flat, unsigned k, float* hi, float* lo) {
+  const size_t dim = size_t(1) << k;
+  std::vector<std::complex<double>> U(dim * dim);
+  for (size_t e = 0; e < dim * dim; ++e) U[e] = std::complex<double>(U_flat[2 * e], U_flat[2 * e + 1]);
+  hq::umma_pack_matrix(U.data(), k, hi, lo);
+}
+
 }  // extern "C"

@@ -164,3 +164,30 @@ def test_tcgen05_lane_map_exhaustive(tmp_path):
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["failures"] == 0 and res["target_sets"] >= 2200 and res["with_chunk_lanes"] > 1000
     assert res["lines_per_quarter_memory_order_map"] < 0.6 * res["lines_per_quarter_rows_map"]
+
+
+def test_tcgen05_operand_blocks_of_a_matrix():
+    """umma_pack_matrix (hq_plan.cpp): the real form of U as K-major 16-byte units, split into TF32 hi / lo.  Checked
+    against a numpy model of the layout: unit (n, c) at index c * R + n holds Bs[n][4c .. 4c + 3], Bs[2i + a][2j + b] =
+    the real 2 x 2 block of U[i][j]; hi has 10 mantissa bits, hi + lo reproduces the fp32 entry to 2^-21."""
+    import ctypes
+    from helpers import Emu
+    emu = Emu()
+    rng = np.random.default_rng(8)
+    for k in (4, 5, 6):
+        dim, R = 2 ** k, 2 * 2 ** k
+        U = (rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))) / np.sqrt(dim)
+        flat = np.ascontiguousarray(U.astype(np.complex128).reshape(-1)).view(np.float64)
+        hi = np.zeros(R * R, np.float32)
+        lo = np.zeros(R * R, np.float32)
+        emu.lib.hq_emu_umma_pack(flat.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(k),
+                                 hi.ctypes.data_as(ctypes.c_void_p), lo.ctypes.data_as(ctypes.c_void_p))
+        U32 = U.astype(np.complex64)
+        Bs = np.zeros((R, R), np.float32)
+        Bs[0::2, 0::2], Bs[0::2, 1::2] = U32.real, -U32.imag        # re_out = re * re_in - im * im_in
+        Bs[1::2, 0::2], Bs[1::2, 1::2] = U32.imag, U32.real         # im_out = im * re_in + re * im_in
+        got_hi = hi.reshape(R // 4, R, 4).transpose(1, 0, 2).reshape(R, R)          # [c][n][e] -> [n][4c + e]
+        got_lo = lo.reshape(R // 4, R, 4).transpose(1, 0, 2).reshape(R, R)
+        assert np.all((got_hi.view(np.uint32) & 0x1fff) == 0) and np.all((got_lo.view(np.uint32) & 0x1fff) == 0)
+        assert np.abs(got_hi - Bs).max() <= 2.0 ** -11 * np.abs(Bs).max()
+        assert np.abs(got_hi.astype(np.float64) + got_lo - Bs).max() <= 2.0 ** -21 * np.abs(Bs).max()
